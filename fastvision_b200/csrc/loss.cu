@@ -1,0 +1,475 @@
+// K4: YOLOv3 target assignment + loss, fused (replaces ~200 ATen launches and >=6 host syncs of
+// loss/yolov3_loss.py:29-124).
+//
+//   loss_prep      : are the labels grouped by image (collate_fn order)?  -> lets the duplicate-cell
+//                    scan stop early; any order stays correct.
+//   loss_match     : one warp per (level, target, anchor): ratio test, cell, coalesced gather of the
+//                    matched raw row, class BCE (lanes over classes, shuffle reduction), CIoU box
+//                    term, IoU objectness target with the reference's "last write wins" rule for
+//                    duplicate cells resolved deterministically.
+//   conf_stream    : (only when the decode kernel did not already fuse it) zero-target objectness
+//                    BCE over every cell -- the one HBM-streaming part of the loss.
+//   loss_finalize  : fixed-order fp64 reduction of all partials -> {S_cls,S_box,S_conf,M} per level
+//                    (what data-parallel ranks all-reduce) and, optionally, the scalar.
+// The objectness sum is  sum_cells bce(p,0) + sum_winners (bce(p,iou) - bce(p,0)) : the first part
+// is a pure stream, the second touches only matched rows.
+#include "common.cuh"
+
+namespace fvb {
+
+constexpr int kLossThreads = 256;
+constexpr int kStreamRows = 1024;  // rows per conf_stream CTA
+
+struct LossParams {
+  Geom g;
+  const float* labels;
+  int T;
+  double* match_ws;  // [L*T*A][4] = {S_cls, box term, conf correction, matched}
+  int* flags;        // [0] labels grouped by image
+};
+
+__global__ void loss_prep_kernel(const float* labels, int T, int* flags) {
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t + 1 < T; t += blockDim.x)
+    if ((int)labels[(size_t)t * 6] > (int)labels[(size_t)(t + 1) * 6]) bad = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) flags[0] = bad ? 0 : 1;
+}
+
+struct TargetCell {
+  bool match;
+  int b, cls, gx, gy;
+  float offx, offy, tw, th, aw, ah;
+};
+
+// build_target for one (target, anchor) on one level: loss/yolov3_loss.py:88-117.
+__device__ __forceinline__ TargetCell target_cell(const Geom& g, int l, const float* lab, int a) {
+  TargetCell c;
+  const int W = g.W[l], H = g.H[l];
+  const float fw = (float)W, fh = (float)H;
+  const float tx = lab[2] * fw, ty = lab[3] * fh;  // :94-95  y_true[:, 2:] * [W,H,W,H]
+  c.tw = lab[4] * fw;
+  c.th = lab[5] * fh;
+  c.aw = g.aw[l][a] / g.stride[l];  // :88-89 anchors in feature units
+  c.ah = g.ah[l][a] / g.stride[l];
+  const float rw = c.tw / c.aw, rh = c.th / c.ah;  // :98
+  const float m = fmaxf(fmaxf(rw, 1.0f / rw), fmaxf(rh, 1.0f / rh));
+  c.match = m < 4.0f;  // :99
+  c.b = (int)lab[0];
+  c.cls = (int)lab[1];
+  const float fx = floorf(tx), fy = floorf(ty);  // :113
+  c.offx = tx - fx;                              // :114 (before the clamp)
+  c.offy = ty - fy;
+  // clamp in float first so that a huge coordinate cannot overflow the int conversion
+  c.gx = (int)fminf(fmaxf(fx, 0.0f), (float)(W - 1));  // :116
+  c.gy = (int)fminf(fmaxf(fy, 0.0f), (float)(H - 1));  // :117
+  return c;
+}
+
+__global__ void __launch_bounds__(kLossThreads) loss_match_kernel(const LossParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * kLossThreads + threadIdx.x) >> 5;
+  const int TA = p.T * p.g.A;
+  if (wid >= (long long)p.g.L * TA) return;
+  const int l = (int)(wid / TA);
+  const int ta = (int)(wid - (long long)l * TA);
+  const int t = ta / p.g.A, a = ta - t * p.g.A;
+  double* out = p.match_ws + (size_t)wid * 4;
+
+  const TargetCell c = target_cell(p.g, l, p.labels + (size_t)t * 6, a);
+  if (!c.match || c.b < 0 || c.b >= p.g.B) {  // (an out-of-range batch index raises in the reference)
+    if (lane < 4) out[lane] = 0.0;
+    return;
+  }
+  const int K = p.g.K, C = K - 5;
+  const float* row = p.g.head[l] + ((((size_t)c.b * p.g.A + a) * p.g.H[l] + c.gy) * p.g.W[l] + c.gx) * K;
+
+  // class BCE over the matched row (:50-52), lanes over channels
+  float first = lane < K ? row[lane] : 0.0f;  // channels 0..31 (K >= 6)
+  double s_cls = 0.0;
+  for (int ch = lane; ch < K; ch += 32) {
+    float v = ch < 32 ? first : row[ch];
+    if (ch >= 5) {
+      float prob = sigmoid_precise(v);
+      float tgt = (ch - 5 == c.cls) ? 1.0f : 0.0f;
+      s_cls += (double)bce_term(prob, tgt);
+    }
+  }
+  s_cls = warp_sum(s_cls);
+  (void)C;
+
+  const float r0 = __shfl_sync(0xffffffffu, first, 0), r1 = __shfl_sync(0xffffffffu, first, 1);
+  const float r2 = __shfl_sync(0xffffffffu, first, 2), r3 = __shfl_sync(0xffffffffu, first, 3);
+  const float r4 = __shfl_sync(0xffffffffu, first, 4);
+
+  // duplicate cells: targets_conf[...] = iou (:61) keeps the LAST match in (t,a) order on CPU.
+  // This match loses iff a later target of the same image hits the same cell with the same anchor.
+  const bool grouped = p.flags[0] != 0;
+  bool loser = false;
+  for (int t2b = t + 1; t2b < p.T; t2b += 32) {
+    int t2 = t2b + lane;
+    bool hit = false;
+    int b2 = 0x7fffffff;
+    if (t2 < p.T) {
+      const float* lab2 = p.labels + (size_t)t2 * 6;
+      b2 = (int)lab2[0];
+      if (b2 == c.b) {
+        TargetCell c2 = target_cell(p.g, l, lab2, a);
+        hit = c2.match && c2.gx == c.gx && c2.gy == c.gy;
+      }
+    }
+    if (__any_sync(0xffffffffu, hit)) {
+      loser = true;
+      break;
+    }
+    // grouped labels: once a whole row of 32 is past image b nothing later can collide
+    if (grouped && __all_sync(0xffffffffu, b2 > c.b)) break;
+  }
+
+  if (lane == 0) {
+    // predicted box in cell units (:54-56) vs [offset, wh] (:57), both xywh (:58,:60)
+    float px = sigmoid_precise(r0), py = sigmoid_precise(r1);
+    float pw = expf(r2) * c.aw, ph = expf(r3) * c.ah;
+    Box pb = xywh_to_xyxy(px, py, pw, ph);
+    Box tb = xywh_to_xyxy(c.offx, c.offy, c.tw, c.th);
+    const float eps = 1e-7f;
+    float ciou = iou_family<false>(pb, tb, FVB_CIOU, FVB_VARIANT_LIB, eps);
+    float iou = iou_plain<true>(pb, tb, eps);
+    double conf_corr = 0.0;
+    if (!loser) {
+      float pc = sigmoid_precise(r4);
+      conf_corr = (double)bce_term(pc, iou) - (double)bce_term(pc, 0.0f);
+    }
+    out[0] = s_cls;
+    out[1] = (double)(1.0f - ciou);
+    out[2] = conf_corr;
+    out[3] = 1.0;
+  }
+}
+
+// zero-target objectness BCE, one thread per cell row; partials [L][B][chunks_l]
+struct StreamParams {
+  Geom g;
+  int chunk_off[FVB_MAX_LEVELS + 1];  // first partial of each level
+  int chunks[FVB_MAX_LEVELS];         // chunks per image on each level
+  double* partials;
+};
+
+__global__ void __launch_bounds__(256) conf_stream_kernel(const StreamParams p) {
+  // blockIdx.x enumerates (level, image, chunk)
+  int id = blockIdx.x, l = 0;
+#pragma unroll
+  for (int i = 0; i < FVB_MAX_LEVELS - 1; ++i)
+    if (i < p.g.L - 1 && id >= p.chunk_off[i + 1]) l = i + 1;
+  id -= p.chunk_off[l];
+  const int b = id / p.chunks[l], ch = id - b * p.chunks[l];
+  const int rows = p.g.A * p.g.HW[l];
+  const float* base = p.g.head[l] + (size_t)b * rows * p.g.K + 4;
+  float acc = 0.0f;
+  const int r0 = ch * kStreamRows;
+#pragma unroll
+  for (int i = 0; i < kStreamRows / 256; ++i) {
+    int r = r0 + i * 256 + threadIdx.x;
+    if (r < rows) acc += bce_term(sigmoid_precise(__ldg(base + (size_t)r * p.g.K)), 0.0f);
+  }
+  __shared__ double scratch[32];
+  double s = block_sum((double)acc, scratch);
+  if (threadIdx.x == 0) p.partials[blockIdx.x] = s;
+}
+
+struct FinalizeParams {
+  Geom g;
+  int T;
+  const double* match_ws;
+  const double* conf0;  // decode layout [B][tiles_per_image] (mode 0) or stream layout (mode 1)
+  int conf_mode;
+  int tiles_per_image;
+  int level_begin[FVB_MAX_LEVELS];  // mode 0: tile range inside an image; mode 1: partial range
+  int level_end[FVB_MAX_LEVELS];
+  double* partials;  // [L][4]
+  float* out_loss;
+  float r_box, r_conf, r_cls;
+  long long batch_global;
+};
+
+__device__ __forceinline__ float combine_loss(const Geom& g, const double* partials, long long batch_global,
+                                              float r_box, float r_conf, float r_cls) {
+  double tot = 0.0;
+  const int C = g.K - 5;
+  for (int l = 0; l < g.L; ++l) {
+    double s_cls = partials[l * 4 + 0], s_box = partials[l * 4 + 1], s_conf = partials[l * 4 + 2], m = partials[l * 4 + 3];
+    if (m > 0.0) tot += (double)r_cls * s_cls / (m * C) + (double)r_box * s_box / m;  // yolov3_loss.py:49-58
+    double cells = (double)batch_global * g.A * g.HW[l];
+    tot += (double)r_conf * s_conf / cells;                                            // :63-64
+  }
+  return (float)(tot * (double)batch_global);                                          // :66-72
+}
+
+__global__ void __launch_bounds__(1024) loss_finalize_kernel(const FinalizeParams p) {
+  __shared__ double scratch[32];
+  const int TA = p.T * p.g.A;
+  for (int l = 0; l < p.g.L; ++l) {
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    const double* ws = p.match_ws + (size_t)l * TA * 4;
+    for (int i = threadIdx.x; i < TA; i += blockDim.x) {
+      a0 += ws[(size_t)i * 4 + 0];
+      a1 += ws[(size_t)i * 4 + 1];
+      a2 += ws[(size_t)i * 4 + 2];
+      a3 += ws[(size_t)i * 4 + 3];
+    }
+    double c0 = 0;
+    if (p.conf_mode == 0) {
+      int per = p.level_end[l] - p.level_begin[l];
+      long long total = (long long)per * p.g.B;
+      for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        int b = (int)(i / per), k = (int)(i - (long long)b * per);
+        c0 += p.conf0[(size_t)b * p.tiles_per_image + p.level_begin[l] + k];
+      }
+    } else {
+      for (int i = p.level_begin[l] + threadIdx.x; i < p.level_end[l]; i += blockDim.x) c0 += p.conf0[i];
+    }
+    a0 = block_sum(a0, scratch);
+    a1 = block_sum(a1, scratch);
+    a2 = block_sum(a2 + c0, scratch);
+    a3 = block_sum(a3, scratch);
+    if (threadIdx.x == 0) {
+      p.partials[l * 4 + 0] = a0;
+      p.partials[l * 4 + 1] = a1;
+      p.partials[l * 4 + 2] = a2;
+      p.partials[l * 4 + 3] = a3;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && p.out_loss != nullptr)
+    p.out_loss[0] = combine_loss(p.g, p.partials, p.batch_global, p.r_box, p.r_conf, p.r_cls);
+}
+
+struct CombineParams {
+  Geom g;
+  const double* partials;
+  long long batch_global;
+  float r_box, r_conf, r_cls;
+  float* out;
+};
+__global__ void loss_combine_kernel(const CombineParams p) {
+  if (threadIdx.x == 0) p.out[0] = combine_loss(p.g, p.partials, p.batch_global, p.r_box, p.r_conf, p.r_cls);
+}
+
+// ---- build_target as an API of its own (padded, optionally compacted in (t,a) order) ---------------------
+struct BuildTargetParams {
+  Geom g;
+  int level;
+  const float* labels;
+  int T;
+  int compact;
+  long long *b, *gxy, *a, *cls;
+  float *xywh, *anchor;
+  unsigned char* match;
+  int* count;
+};
+
+__global__ void __launch_bounds__(1024) build_target_kernel(const BuildTargetParams p) {
+  __shared__ uint32_t warp_tot[33];
+  __shared__ uint32_t carry;
+  const int TA = p.T * p.g.A;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < TA; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    TargetCell c;
+    c.match = false;
+    int t = 0, a = 0;
+    if (i < TA) {
+      t = i / p.g.A;
+      a = i - t * p.g.A;
+      c = target_cell(p.g, p.level, p.labels + (size_t)t * 6, a);
+    }
+    // block exclusive scan of the match flags (1024 threads = 32 warps)
+    uint32_t v = c.match ? 1u : 0u, inc = v;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t tv = warp_tot[lane], ti = tv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += u;
+      }
+      warp_tot[lane] = ti - tv;
+      if (lane == 31) warp_tot[32] = ti;
+    }
+    __syncthreads();
+    uint32_t pos = carry + warp_tot[warp] + inc - v;
+    if (i < TA) {
+      p.match[i] = c.match ? 1 : 0;
+      int o = p.compact ? (c.match ? (int)pos : -1) : i;
+      if (o >= 0) {
+        p.b[o] = c.b;
+        p.gxy[(size_t)o * 2 + 0] = c.gx;
+        p.gxy[(size_t)o * 2 + 1] = c.gy;
+        p.a[o] = a;
+        p.cls[o] = c.cls;
+        p.xywh[(size_t)o * 4 + 0] = c.offx;
+        p.xywh[(size_t)o * 4 + 1] = c.offy;
+        p.xywh[(size_t)o * 4 + 2] = c.tw;
+        p.xywh[(size_t)o * 4 + 3] = c.th;
+        p.anchor[(size_t)o * 2 + 0] = c.aw;
+        p.anchor[(size_t)o * 2 + 1] = c.ah;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_tot[32];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p.count[0] = (int)carry;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int stream_chunks(const Geom& g, int l) { return (g.A * g.HW[l] + kStreamRows - 1) / kStreamRows; }
+
+}  // namespace fvb
+
+using namespace fvb;
+
+extern "C" size_t fvb_yolov3_loss_workspace_bytes(const fvb_yolo_geom* geom, int64_t num_labels) {
+  Geom g;
+  if (make_geom(geom, nullptr, &g) != FVB_OK) return 0;
+  size_t o = 256;  // flags
+  o = align_up(o + (size_t)g.L * (size_t)num_labels * g.A * 4 * 8, 256);
+  size_t parts = 0;
+  for (int l = 0; l < g.L; ++l) parts += (size_t)stream_chunks(g, l) * g.B;
+  o = align_up(o + parts * 8, 256);
+  return o + 256;
+}
+
+extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                   int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                                   const double* d_conf_bce0, double* d_partials, float* d_out_loss, void* d_ws,
+                                   void* stream) {
+  FVB_REQUIRE(d_heads && d_partials && d_ws, "yolov3_loss: NULL pointer");
+  FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "yolov3_loss: num_labels=%lld", (long long)num_labels);
+  FVB_REQUIRE(num_labels == 0 || d_labels, "yolov3_loss: labels NULL");
+  FVB_REQUIRE(((uintptr_t)d_ws & 255) == 0, "yolov3_loss: workspace must be 256-byte aligned");
+  LossParams lp;
+  int rc = make_geom(geom, d_heads, &lp.g);
+  if (rc != FVB_OK) return rc;
+  for (int l = 0; l < lp.g.L; ++l) FVB_REQUIRE(d_heads[l] != nullptr, "yolov3_loss: head %d is NULL", l);
+  FVB_REQUIRE(lp.g.B >= 1, "yolov3_loss: empty batch");
+  const Geom& g = lp.g;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* w = (unsigned char*)d_ws;
+  lp.flags = (int*)w;
+  size_t o = 256;
+  lp.match_ws = (double*)(w + o);
+  o = align_up(o + (size_t)g.L * (size_t)num_labels * g.A * 4 * 8, 256);
+  double* stream_parts = (double*)(w + o);
+  lp.labels = d_labels;
+  lp.T = (int)num_labels;
+
+  if (lp.T > 0) {
+    loss_prep_kernel<<<1, 1024, 0, s>>>(d_labels, lp.T, lp.flags);
+    long long warps = (long long)g.L * lp.T * g.A;
+    long long blocks = (warps * 32 + kLossThreads - 1) / kLossThreads;
+    loss_match_kernel<<<(unsigned)blocks, kLossThreads, 0, s>>>(lp);
+    count_launch(2);
+  }
+
+  FinalizeParams fp;
+  fp.g = g;
+  fp.T = lp.T;
+  fp.match_ws = lp.match_ws;
+  fp.partials = d_partials;
+  fp.out_loss = d_out_loss;
+  fp.r_box = ratio_box;
+  fp.r_conf = ratio_conf;
+  fp.r_cls = ratio_cls;
+  fp.batch_global = g.B;
+  if (d_conf_bce0) {
+    fp.conf0 = d_conf_bce0;
+    fp.conf_mode = 0;
+    int t = 0;
+    for (int l = 0; l < g.L; ++l) {
+      fp.level_begin[l] = t;
+      t += decode_tiles_level(g, l);
+      fp.level_end[l] = t;
+    }
+    fp.tiles_per_image = t;
+  } else {
+    StreamParams sp;
+    sp.g = g;
+    int t = 0;
+    for (int l = 0; l < g.L; ++l) {
+      sp.chunk_off[l] = t;
+      sp.chunks[l] = stream_chunks(g, l);
+      fp.level_begin[l] = t;
+      t += sp.chunks[l] * g.B;
+      fp.level_end[l] = t;
+    }
+    for (int l = g.L; l <= FVB_MAX_LEVELS; ++l) sp.chunk_off[l] = t;
+    sp.partials = stream_parts;
+    conf_stream_kernel<<<t, 256, 0, s>>>(sp);
+    count_launch();
+    fp.conf0 = stream_parts;
+    fp.conf_mode = 1;
+    fp.tiles_per_image = 0;
+  }
+  loss_finalize_kernel<<<1, 1024, 0, s>>>(fp);
+  count_launch();
+  return check_launch("yolov3_loss");
+}
+
+extern "C" int fvb_yolov3_loss_combine_f32(const fvb_yolo_geom* geom, int64_t batch_global, const double* d_partials,
+                                           float ratio_box, float ratio_conf, float ratio_cls, float* d_out_loss,
+                                           void* stream) {
+  FVB_REQUIRE(d_partials && d_out_loss, "loss_combine: NULL pointer");
+  FVB_REQUIRE(batch_global >= 1, "loss_combine: batch_global=%lld", (long long)batch_global);
+  CombineParams p;
+  int rc = make_geom(geom, nullptr, &p.g);
+  if (rc != FVB_OK) return rc;
+  p.partials = d_partials;
+  p.batch_global = batch_global;
+  p.r_box = ratio_box;
+  p.r_conf = ratio_conf;
+  p.r_cls = ratio_cls;
+  p.out = d_out_loss;
+  loss_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return check_launch("loss_combine_kernel");
+}
+
+extern "C" int fvb_yolov3_build_target_f32(const fvb_yolo_geom* geom, int level, const float* d_labels,
+                                           int64_t num_labels, int compact, int64_t* d_b, int64_t* d_gxy, int64_t* d_a,
+                                           int64_t* d_cls, float* d_xywh, float* d_anchor, uint8_t* d_match,
+                                           int32_t* d_count, void* stream) {
+  BuildTargetParams p;
+  int rc = make_geom(geom, nullptr, &p.g);
+  if (rc != FVB_OK) return rc;
+  FVB_REQUIRE(level >= 0 && level < p.g.L, "build_target: level %d", level);
+  FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "build_target: num_labels");
+  FVB_REQUIRE(d_count && (num_labels == 0 || (d_labels && d_b && d_gxy && d_a && d_cls && d_xywh && d_anchor && d_match)),
+              "build_target: NULL pointer");
+  p.level = level;
+  p.labels = d_labels;
+  p.T = (int)num_labels;
+  p.compact = compact;
+  p.b = (long long*)d_b;
+  p.gxy = (long long*)d_gxy;
+  p.a = (long long*)d_a;
+  p.cls = (long long*)d_cls;
+  p.xywh = d_xywh;
+  p.anchor = d_anchor;
+  p.match = d_match;
+  p.count = d_count;
+  build_target_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return check_launch("build_target_kernel");
+}

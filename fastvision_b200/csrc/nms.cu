@@ -1,0 +1,401 @@
+// K3: confidence filter + NMS for every image of a batch in ONE launch (one CTA per image).
+//
+// Replaces the per-image Python loop of the reference (utils/fit.py:94-95) around
+// non_max_suppression (detection/tools/NMS.py:5-23; demo flavours demos/yolov3_u/utils/nms.py) and
+// the third-party torchvision.ops.nms it calls.  Phases, all inside one CTA:
+//   0  candidates: popcount/scan of the image's candidate bitmap (written by the decode kernel, or
+//      built here from results[...,4] > conf_thr) -> rows in ascending order = the reference's
+//      boolean-mask order, so "slot" order is the tie-break order of its stable sort;
+//   1  one warp per candidate: coalesced read of the decoded row, cls*conf products, warp arg-max
+//      (first maximum), xywh->xyxy, optional class gap (box + cat*max_wh in fp32);
+//   2  block radix sort of (rank desc, slot asc) keys;
+//   3  chunked greedy suppression with a kept list (nms.cuh);
+//   4  padded outputs + count; consumed bitmap words are cleared for the next step.
+// Candidates live in shared memory up to kCapS per image; beyond that the same code runs on a
+// global workspace slice (slower, still exact) so there is no overflow case.
+#include "nms.cuh"
+
+#include <math.h>
+
+namespace fvb {
+
+constexpr int kCapS = 2048;  // candidates per image held in shared memory
+
+struct YoloNmsParams {
+  const float* results;
+  int B, N, K;
+  float conf_thr, iou_thr;
+  int max_det, flavour;
+  float max_wh;
+  int max_nms;
+  uint32_t* bitmap;  // [B, words]; either caller-provided (decode) or a workspace slice
+  int words;
+  int build_bitmap;  // scan results[...,4] here
+  int clear_bitmap;
+  float* out_boxes;
+  float* out_scores;
+  long long* out_cls;
+  int* out_rows;
+  int* out_cnt;
+  // global fallback, per image strides of N entries
+  unsigned long long* ws_keys;  // [B][2][N]
+  float4* ws_box;               // [B][N]
+  float* ws_score;              // [B][N]
+  int* ws_cat;                  // [B][N]
+  int* ws_row;                  // [B][N]
+};
+
+struct NmsSmemLayout {
+  size_t keys0, keys1, box, score, cat, row, cnt, warp_tot, kbox, karea, kslot, gs, misc, total;
+};
+
+__host__ __device__ inline NmsSmemLayout nms_layout(int cap, int max_keep) {
+  NmsSmemLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes, size_t align) {
+    o = (o + align - 1) / align * align;
+    size_t r = o;
+    o += bytes;
+    return r;
+  };
+  L.keys0 = take((size_t)cap * 8, 16);
+  L.keys1 = take((size_t)cap * 8, 16);
+  L.box = take((size_t)cap * 16, 16);
+  L.score = take((size_t)cap * 4, 16);
+  L.cat = take((size_t)cap * 4, 16);
+  L.row = take((size_t)cap * 4, 16);
+  L.cnt = take((size_t)kNmsWarps * 256 * 4, 16);
+  L.warp_tot = take((size_t)(kNmsWarps + 1) * 4, 16);
+  L.kbox = take((size_t)max_keep * 16, 16);
+  L.karea = take((size_t)max_keep * 4, 16);
+  L.kslot = take((size_t)max_keep * 4, 16);
+  L.gs = take(sizeof(GreedyShared), 16);
+  L.misc = take(64, 16);
+  L.total = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const NmsSmemLayout L = nms_layout(kCapS, p.max_det);
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L.cnt);
+  uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + L.warp_tot);
+  float4* kbox = reinterpret_cast<float4*>(smem + L.kbox);
+  float* karea = reinterpret_cast<float*>(smem + L.karea);
+  int* kslot = reinterpret_cast<int*>(smem + L.kslot);
+  GreedyShared* gs = reinterpret_cast<GreedyShared*>(smem + L.gs);
+  int* misc = reinterpret_cast<int*>(smem + L.misc);  // [0] n_valid
+
+  const float* res = p.results + (size_t)b * p.N * p.K;
+  uint32_t* bm = p.bitmap + (size_t)b * p.words;
+
+  // ---- phase 0': build the bitmap from the objectness channel (stand-alone use) ----------------------
+  if (p.build_bitmap) {
+    for (int w0 = warp; w0 < p.words; w0 += kNmsWarps) {
+      int r = w0 * 32 + lane;
+      bool c = (r < p.N) && (res[(size_t)r * p.K + 4] > p.conf_thr);
+      unsigned m = __ballot_sync(0xffffffffu, c);
+      if (lane == 0) bm[w0] = m;
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 0: ordered candidate rows from the bitmap -------------------------------------------------
+  const int wpt = (p.words + kNmsThreads - 1) / kNmsThreads;
+  const int wbeg = min(p.words, (int)threadIdx.x * wpt), wend = min(p.words, wbeg + wpt);
+  uint32_t my = 0;
+  for (int w = wbeg; w < wend; ++w) my += __popc(bm[w]);
+  uint32_t base = block_exclusive_scan(my, warp_tot);
+  const int n = (int)warp_tot[kNmsWarps];
+  __syncthreads();  // warp_tot is reused by the sort
+
+  unsigned long long *keys0, *keys1;
+  float4* sbox;
+  float* sscore;
+  int *scat, *srow;
+  if (n <= kCapS) {
+    keys0 = reinterpret_cast<unsigned long long*>(smem + L.keys0);
+    keys1 = reinterpret_cast<unsigned long long*>(smem + L.keys1);
+    sbox = reinterpret_cast<float4*>(smem + L.box);
+    sscore = reinterpret_cast<float*>(smem + L.score);
+    scat = reinterpret_cast<int*>(smem + L.cat);
+    srow = reinterpret_cast<int*>(smem + L.row);
+  } else {
+    keys0 = p.ws_keys + (size_t)b * 2 * p.N;
+    keys1 = keys0 + p.N;
+    sbox = p.ws_box + (size_t)b * p.N;
+    sscore = p.ws_score + (size_t)b * p.N;
+    scat = p.ws_cat + (size_t)b * p.N;
+    srow = p.ws_row + (size_t)b * p.N;
+  }
+  {
+    uint32_t pos = base;
+    for (int w = wbeg; w < wend; ++w) {
+      uint32_t bits = bm[w];
+      while (bits) {
+        int bit = __ffs(bits) - 1;
+        bits &= bits - 1;
+        srow[pos++] = w * 32 + bit;
+      }
+    }
+  }
+  if (threadIdx.x == 0) misc[0] = 0;
+  __syncthreads();
+  if (p.clear_bitmap)
+    for (int w = threadIdx.x; w < p.words; w += kNmsThreads) bm[w] = 0u;
+
+  if (n == 0) {
+    if (threadIdx.x == 0) p.out_cnt[b] = 0;
+    return;
+  }
+
+  // ---- phase 1: score / class / box per candidate (warp per candidate) ---------------------------------
+  int valid_local = 0;
+  for (int i = warp; i < n; i += kNmsWarps) {
+    const float* row = res + (size_t)srow[i] * p.K;
+    float conf = row[4];
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    for (int c = 5 + lane; c < p.K; c += 32) {
+      float v = row[c] * conf;  // prediction[:, 5:] *= prediction[:, 4:5]  (NMS.py:13)
+      if (v > best) {
+        best = v;
+        bidx = c - 5;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) {
+        best = ov;
+        bidx = oi;
+      }
+    }
+    if (lane == 0) {
+      float x = row[0], y = row[1], w = row[2], h = row[3];
+      Box bx;
+      if (p.flavour == FVB_NMS_DEMO) {  // boxes arrive as xyxy (demos/yolov3_u/utils/nms.py:8)
+        bx.x1 = x; bx.y1 = y; bx.x2 = w; bx.y2 = h;
+      } else {
+        bx = xywh_to_xyxy(x, y, w, h);
+      }
+      float rank = (p.flavour == FVB_NMS_DEMO) ? conf : best;
+      bool ok = true;
+      if (p.flavour == FVB_NMS_DEMO_BATCH) ok = best > p.conf_thr;  // nms.py:80 second filter on the score
+      if (p.flavour != FVB_NMS_LIB) {
+        float gap = (float)bidx * p.max_wh;  // nms.py:44-45, fp32
+        bx.x1 += gap; bx.y1 += gap; bx.x2 += gap; bx.y2 += gap;
+      }
+      sbox[i] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+      sscore[i] = rank;
+      scat[i] = bidx;
+      uint32_t hi = ok ? desc_key(rank) : 0xffffffffu;
+      keys0[i] = ((unsigned long long)hi << 32) | (uint32_t)i;
+      valid_local += ok ? 1 : 0;
+    }
+  }
+  if (lane == 0 && valid_local) atomicAdd(&misc[0], valid_local);
+  __syncthreads();
+  const int n_use = min(misc[0], p.max_nms);
+
+  // ---- phase 2 + 3 ---------------------------------------------------------------------------------------
+  unsigned long long* sorted = block_radix_sort_hi32(keys0, keys1, n, cnt, warp_tot);
+  int kept = block_greedy_nms(sorted, n_use, sbox, p.iou_thr, p.max_det, kbox, karea, kslot, gs);
+
+  // ---- phase 4: padded outputs -------------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < kept; i += kNmsThreads) {
+    int slot = kslot[i];
+    int r = srow[slot];
+    const float* row = res + (size_t)r * p.K;
+    float x = row[0], y = row[1], w = row[2], h = row[3];
+    Box bx;
+    if (p.flavour == FVB_NMS_DEMO) {
+      bx.x1 = x; bx.y1 = y; bx.x2 = w; bx.y2 = h;
+    } else {
+      bx = xywh_to_xyxy(x, y, w, h);
+    }
+    size_t o = (size_t)b * p.max_det + i;
+    reinterpret_cast<float4*>(p.out_boxes)[o] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+    p.out_scores[o] = sscore[slot];
+    p.out_cls[o] = (long long)scat[slot];
+    if (p.out_rows) p.out_rows[o] = r;
+  }
+  if (threadIdx.x == 0) p.out_cnt[b] = kept;
+}
+
+// ---- segmented NMS: the torchvision.ops.nms equivalent, one CTA per segment ---------------------------------
+struct SegNmsParams {
+  const float* boxes;
+  const float* scores;
+  const int* seg_off;
+  float iou_thr;
+  int max_keep;
+  int* keep_idx;
+  int* keep_cnt;
+  unsigned long long* ws_keys;  // [2 * total]
+  float4* ws_box;               // [total]
+};
+
+__global__ void __launch_bounds__(kNmsThreads) seg_nms_kernel(const SegNmsParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const NmsSmemLayout L = nms_layout(kCapS, p.max_keep);
+  const int s = blockIdx.x;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L.cnt);
+  uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + L.warp_tot);
+  float4* kbox = reinterpret_cast<float4*>(smem + L.kbox);
+  float* karea = reinterpret_cast<float*>(smem + L.karea);
+  int* kslot = reinterpret_cast<int*>(smem + L.kslot);
+  GreedyShared* gs = reinterpret_cast<GreedyShared*>(smem + L.gs);
+  const int beg = p.seg_off[s], n = p.seg_off[s + 1] - beg;
+  if (n <= 0) {
+    if (threadIdx.x == 0) p.keep_cnt[s] = 0;
+    return;
+  }
+  unsigned long long *keys0, *keys1;
+  float4* sbox;
+  if (n <= kCapS) {
+    keys0 = reinterpret_cast<unsigned long long*>(smem + L.keys0);
+    keys1 = reinterpret_cast<unsigned long long*>(smem + L.keys1);
+    sbox = reinterpret_cast<float4*>(smem + L.box);
+  } else {
+    keys0 = p.ws_keys + (size_t)2 * beg;
+    keys1 = keys0 + n;
+    sbox = p.ws_box + beg;
+  }
+  for (int i = threadIdx.x; i < n; i += kNmsThreads) {
+    const float* bp = p.boxes + (size_t)(beg + i) * 4;
+    sbox[i] = make_float4(bp[0], bp[1], bp[2], bp[3]);
+    keys0[i] = ((unsigned long long)desc_key(p.scores[beg + i]) << 32) | (uint32_t)i;
+  }
+  __syncthreads();
+  unsigned long long* sorted = block_radix_sort_hi32(keys0, keys1, n, cnt, warp_tot);
+  int kept = block_greedy_nms(sorted, n, sbox, p.iou_thr, p.max_keep, kbox, karea, kslot, gs);
+  for (int i = threadIdx.x; i < kept; i += kNmsThreads) p.keep_idx[(size_t)s * p.max_keep + i] = kslot[i];
+  if (threadIdx.x == 0) p.keep_cnt[s] = kept;
+}
+
+// fp32 threshold t such that (x > t) in fp32  <=>  ((double)x > thr) -- torchvision's CPU op compares
+// the fp32 ratio against the double threshold.
+static float thr_round_down(double thr) {
+  float t = (float)thr;
+  if ((double)t > thr) t = nextafterf(t, -INFINITY);
+  return t;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int ensure_smem(const void* fn, size_t bytes, const char* what) {
+  if (bytes > 227 * 1024) {
+    set_error("%s: %zu bytes of shared memory needed (max_det/max_keep too large)", what, bytes);
+    return FVB_E_LIMIT;
+  }
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%zu): %s", what, bytes, cudaGetErrorString(e));
+    return FVB_E_CUDA;
+  }
+  return FVB_OK;
+}
+
+}  // namespace fvb
+
+using namespace fvb;
+
+extern "C" size_t fvb_yolo_nms_workspace_bytes(int batch, int rows_per_image) {
+  size_t bn = (size_t)batch * (size_t)rows_per_image;
+  size_t words = ((size_t)rows_per_image + 31) / 32;
+  size_t o = 0;
+  o = align_up(o + bn * 2 * 8, 256);            // keys
+  o = align_up(o + bn * 16, 256);               // boxes
+  o = align_up(o + bn * 4, 256);                // score
+  o = align_up(o + bn * 4, 256);                // cat
+  o = align_up(o + bn * 4, 256);                // row
+  o = align_up(o + (size_t)batch * words * 4, 256);  // private bitmap (stand-alone use)
+  return o + 256;
+}
+
+extern "C" int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_image, int channels, float conf_thr,
+                                double iou_thr, int max_det, int flavour, float max_wh, uint32_t* d_cand_bitmap,
+                                int clear_bitmap, float* d_out_boxes, float* d_out_scores, int64_t* d_out_cls,
+                                int32_t* d_out_rows, int32_t* d_out_cnt, void* d_ws, void* stream) {
+  FVB_REQUIRE(batch >= 0 && rows_per_image >= 1 && channels >= 6, "yolo_nms: bad shape B=%d N=%d K=%d", batch, rows_per_image, channels);
+  FVB_REQUIRE(max_det >= 1, "yolo_nms: max_det=%d", max_det);
+  FVB_REQUIRE(flavour >= FVB_NMS_LIB && flavour <= FVB_NMS_DEMO_BATCH, "yolo_nms: unknown flavour %d", flavour);
+  FVB_REQUIRE(d_results && d_out_boxes && d_out_scores && d_out_cls && d_out_cnt && d_ws, "yolo_nms: NULL pointer");
+  FVB_REQUIRE(((uintptr_t)d_out_boxes & 15) == 0 && ((uintptr_t)d_ws & 255) == 0, "yolo_nms: out_boxes must be 16-byte and workspace 256-byte aligned");
+  if (batch == 0) return FVB_OK;
+  YoloNmsParams p;
+  p.results = d_results;
+  p.B = batch;
+  p.N = rows_per_image;
+  p.K = channels;
+  p.conf_thr = conf_thr;
+  p.iou_thr = thr_round_down(iou_thr);
+  p.max_det = max_det;
+  p.flavour = flavour;
+  p.max_wh = max_wh;
+  p.max_nms = 30000;  // demos/yolov3_u/utils/nms.py:16
+  p.words = (rows_per_image + 31) / 32;
+  size_t bn = (size_t)batch * (size_t)rows_per_image;
+  unsigned char* w = (unsigned char*)d_ws;
+  size_t o = 0;
+  p.ws_keys = (unsigned long long*)(w + o); o = align_up(o + bn * 2 * 8, 256);
+  p.ws_box = (float4*)(w + o);              o = align_up(o + bn * 16, 256);
+  p.ws_score = (float*)(w + o);             o = align_up(o + bn * 4, 256);
+  p.ws_cat = (int*)(w + o);                 o = align_up(o + bn * 4, 256);
+  p.ws_row = (int*)(w + o);                 o = align_up(o + bn * 4, 256);
+  if (d_cand_bitmap) {
+    p.bitmap = d_cand_bitmap;
+    p.build_bitmap = 0;
+    p.clear_bitmap = clear_bitmap;
+  } else {
+    p.bitmap = (uint32_t*)(w + o);
+    p.build_bitmap = 1;
+    p.clear_bitmap = 0;
+  }
+  p.out_boxes = d_out_boxes;
+  p.out_scores = d_out_scores;
+  p.out_cls = (long long*)d_out_cls;
+  p.out_rows = d_out_rows;
+  p.out_cnt = d_out_cnt;
+  NmsSmemLayout L = nms_layout(kCapS, max_det);
+  int rc = ensure_smem((const void*)yolo_nms_kernel, L.total, "yolo_nms");
+  if (rc != FVB_OK) return rc;
+  yolo_nms_kernel<<<batch, kNmsThreads, L.total, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return check_launch("yolo_nms_kernel");
+}
+
+extern "C" size_t fvb_nms_segmented_workspace_bytes(int64_t total_boxes, int segments) {
+  (void)segments;
+  return align_up((size_t)total_boxes * 16, 256) + align_up((size_t)total_boxes * 16, 256) + 256;
+}
+
+extern "C" int fvb_nms_segmented_f32(const float* d_boxes, const float* d_scores, const int32_t* d_seg_offsets,
+                                     int segments, int64_t total_boxes, double iou_thr, int max_keep,
+                                     int32_t* d_keep_idx, int32_t* d_keep_cnt, void* d_ws, void* stream) {
+  FVB_REQUIRE(segments >= 0 && total_boxes >= 0 && max_keep >= 1, "nms_segmented: bad sizes");
+  FVB_REQUIRE(d_seg_offsets && d_keep_idx && d_keep_cnt && d_ws, "nms_segmented: NULL pointer");
+  FVB_REQUIRE(total_boxes == 0 || (d_boxes && d_scores), "nms_segmented: NULL boxes/scores");
+  FVB_REQUIRE(((uintptr_t)d_ws & 255) == 0, "nms_segmented: workspace must be 256-byte aligned");
+  if (segments == 0) return FVB_OK;
+  SegNmsParams p;
+  p.boxes = d_boxes;
+  p.scores = d_scores;
+  p.seg_off = d_seg_offsets;
+  p.iou_thr = thr_round_down(iou_thr);
+  p.max_keep = max_keep;
+  p.keep_idx = d_keep_idx;
+  p.keep_cnt = d_keep_cnt;
+  p.ws_keys = (unsigned long long*)d_ws;
+  p.ws_box = (float4*)((unsigned char*)d_ws + align_up((size_t)total_boxes * 16, 256));
+  NmsSmemLayout L = nms_layout(kCapS, max_keep);
+  int rc = ensure_smem((const void*)seg_nms_kernel, L.total, "nms_segmented");
+  if (rc != FVB_OK) return rc;
+  seg_nms_kernel<<<segments, kNmsThreads, L.total, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return check_launch("seg_nms_kernel");
+}

@@ -1,0 +1,104 @@
+"""YOLOv3 loss -- drop-in for Yolov3Loss, loss/yolov3_loss.py:8-124 (forward only this round).
+
+``forward(y_pred, y_true)`` returns Tensor[1] exactly like the reference; the ~200 ATen launches and
+>=6 host syncs collapse into 3-4 small kernels.  ``partials`` ([L,4] f64: S_cls, S_box, S_conf, M per
+level) is what a data-parallel run all-reduces; ``combine`` turns reduced partials into the
+scalar with the global-batch normalisers.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..detection.models.yolov3 import DecodeContext
+
+
+class Yolov3Loss(nn.Module):
+
+    def __init__(self, model, iou_negative_thres, ratio_box, ratio_conf, ratio_cls):
+        super(Yolov3Loss, self).__init__()
+        if isinstance(model, torch.nn.DataParallel):
+            model = model.module
+        self.anchor_levels = model.anchors_per_level
+        self.backbone_stride_levels = model.backbone_strides_per_level
+        self.levels = len(self.backbone_stride_levels)
+        self.iou_negative_thres = iou_negative_thres       # stored, never used -- as in the reference
+        self.ratio_box = ratio_box
+        self.ratio_conf = ratio_conf
+        self.ratio_cls = ratio_cls
+        self._ctx = None
+        self.partials = None
+
+    def _context(self, y_pred):
+        key = (y_pred[0].size(0), y_pred[0].size(1), y_pred[0].size(4), tuple(int(h.size(2)) for h in y_pred),
+               tuple(int(h.size(3)) for h in y_pred), y_pred[0].device)
+        if self._ctx is None or self._ctx.key != key:
+            self._ctx = DecodeContext(y_pred, self.anchor_levels, self.backbone_stride_levels)
+        return self._ctx
+
+    def forward(self, y_pred, y_true, conf_bce0=None, ctx=None, out=None, partials=None):
+        """y_pred: list of raw [B,A,H,W,K]; y_true [T,6] = [batch_idx, cls, xc, yc, w, h] -> Tensor[1].
+
+        ``conf_bce0``: partials written by ``yolov3_decode(..., want_bce0=True)`` over the same heads; when
+        given the loss does not touch the dense objectness channel again.
+        """
+        heads = [_lib.require_cuda(h, "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
+        labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
+        ctx = ctx or self._context(heads)
+        dev = ctx.device
+        t = labels.size(0)
+        if out is None:
+            out = torch.empty(1, dtype=torch.float32, device=dev)
+        if partials is None:
+            partials = torch.empty(ctx.geom.levels, 4, dtype=torch.float64, device=dev)
+        lib = _lib.load()
+        ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, t), dev, "yolov3_loss")
+        with torch.cuda.device(dev):
+            _lib.check(lib.fvb_yolov3_loss_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
+                                               float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
+                                               _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
+                                               _lib.dptr(ws), _lib.stream()), "yolov3_loss")
+        self.partials = partials
+        return out
+
+    def combine(self, partials, batch_global, ctx=None, out=None):
+        """Scalar loss from (all-reduced) per-level partials with GLOBAL-batch normalisers."""
+        ctx = ctx or self._ctx
+        if out is None:
+            out = torch.empty(1, dtype=torch.float32, device=partials.device)
+        lib = _lib.load()
+        with torch.cuda.device(partials.device):
+            _lib.check(lib.fvb_yolov3_loss_combine_f32(ctx.geom, int(batch_global), _lib.dptr(partials),
+                                                       float(self.ratio_box), float(self.ratio_conf),
+                                                       float(self.ratio_cls), _lib.dptr(out), _lib.stream()), "loss_combine")
+        return out
+
+    def build_target(self, y_pred, y_true):
+        """loss/yolov3_loss.py:75-124 -> (gt_locations, gt_categories, gt_xywh, matched_anchors), matches in (t,a) order."""
+        heads = [_lib.require_cuda(h, "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
+        labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
+        ctx = self._context(heads)
+        dev = ctx.device
+        t, a = labels.size(0), ctx.num_anchors
+        lib = _lib.load()
+        locs, cats, xywhs, anchs = [], [], [], []
+        for lvl in range(ctx.geom.levels):
+            n = t * a
+            b = torch.empty(n, dtype=torch.int64, device=dev)
+            gxy = torch.empty(n, 2, dtype=torch.int64, device=dev)
+            ai = torch.empty(n, dtype=torch.int64, device=dev)
+            cls = torch.empty(n, dtype=torch.int64, device=dev)
+            xywh = torch.empty(n, 4, dtype=torch.float32, device=dev)
+            anc = torch.empty(n, 2, dtype=torch.float32, device=dev)
+            match = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+            count = torch.zeros(1, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.fvb_yolov3_build_target_f32(ctx.geom, lvl, _lib.dptr(labels), t, 1, _lib.dptr(b),
+                                                           _lib.dptr(gxy), _lib.dptr(ai), _lib.dptr(cls), _lib.dptr(xywh),
+                                                           _lib.dptr(anc), _lib.dptr(match), _lib.dptr(count),
+                                                           _lib.stream()), "build_target")
+            m = int(count[0])  # ragged result: the reference syncs at the same point (boolean-mask index, :105)
+            locs.append((b[:m], gxy[:m], ai[:m]))
+            cats.append(cls[:m])
+            xywhs.append(xywh[:m])
+            anchs.append(anc[:m])
+        return locs, cats, xywhs, anchs

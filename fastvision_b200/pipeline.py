@@ -1,0 +1,125 @@
+"""The fused validation step: decode -> NMS (all images) -> loss, i.e. the per-batch body of the
+reference's ``Fit._val`` (utils/fit.py:86-95) without its per-image Python loop and host syncs.
+
+Kernel sequence per step (5 launches, optionally replayed as one CUDA graph):
+    decode (+ NMS candidate bitmap + zero-target objectness BCE partials)      fvb_yolo_decode_f32
+    NMS for every image                                                          fvb_yolo_nms_f32
+    loss_prep, loss_match, loss_finalize                                         fvb_yolov3_loss_f32
+Under ``torch.distributed`` the batch is sharded per image: every rank runs the same step on its slice
+and the only collective is an all-reduce of the L*4 fp64 loss partials; decode and NMS need none.
+"""
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from .detection.models.yolov3 import DecodeContext, yolov3_decode
+from .detection.tools.nms import non_max_suppression_batched
+from .loss.yolov3_loss import Yolov3Loss
+
+
+class _ModelStub:
+    def __init__(self, anchors_per_level, strides):
+        self.anchors_per_level = anchors_per_level
+        self.backbone_strides_per_level = strides
+
+
+class ValStep:
+    def __init__(self, anchors_per_level, strides, conf_thres=0.25, iou_thres=0.45, max_det=300,
+                 ratio_box=0.05, ratio_conf=1.0, ratio_cls=0.5, nms_flavour="lib", precise_decode=False,
+                 process_group=None, batch_global: Optional[int] = None):
+        self.anchors_per_level = anchors_per_level
+        self.strides = strides
+        self.conf_thres, self.iou_thres, self.max_det = conf_thres, iou_thres, max_det
+        self.nms_flavour = nms_flavour
+        self.precise = precise_decode
+        self.loss_fn = Yolov3Loss(_ModelStub(anchors_per_level, strides), 0.5, ratio_box, ratio_conf, ratio_cls)
+        self.pg = process_group
+        self.batch_global = batch_global
+        self.ctx = None
+        self.graph = None
+        self.out = None
+
+    def _prepare(self, heads):
+        ctx = DecodeContext(heads, self.anchors_per_level, self.strides)
+        if self.ctx is not None and self.ctx.key == ctx.key:
+            return
+        self.ctx = ctx
+        dev, b, md = ctx.device, ctx.batch, self.max_det
+        self.out = {
+            "results": torch.empty(b, ctx.rows, ctx.k, dtype=torch.float32, device=dev),
+            "boxes": torch.empty(b, md, 4, dtype=torch.float32, device=dev),
+            "scores": torch.empty(b, md, dtype=torch.float32, device=dev),
+            "cls": torch.empty(b, md, dtype=torch.int64, device=dev),
+            "cnt": torch.zeros(b, dtype=torch.int32, device=dev),
+            "rows": torch.empty(b, md, dtype=torch.int32, device=dev),
+            "loss": torch.empty(1, dtype=torch.float32, device=dev),
+            "partials": torch.empty(ctx.geom.levels, 4, dtype=torch.float64, device=dev),
+        }
+        ctx.bitmap()
+        ctx.bce0()
+        self.graph = None
+
+    def _distributed(self):
+        return self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                       and torch.distributed.get_world_size() > 1)
+
+    def _run(self, heads, labels):
+        ctx, o = self.ctx, self.out
+        yolov3_decode(heads, self.anchors_per_level, self.strides, precise=self.precise, ctx=ctx, out=o["results"],
+                      conf_thres=self.conf_thres, want_bce0=True)
+        non_max_suppression_batched(o["results"], self.conf_thres, self.iou_thres, self.max_det, self.nms_flavour,
+                                    cand_bitmap=ctx.bitmap(), clear_bitmap=True,
+                                    out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]))
+        if self._distributed():
+            self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
+            torch.distributed.all_reduce(o["partials"], group=self.pg)     # 96 bytes; the only collective
+            bg = self.batch_global or ctx.batch * torch.distributed.get_world_size(self.pg)
+            self.loss_fn.combine(o["partials"], bg, ctx=ctx, out=o["loss"])
+        else:
+            self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
+        return o
+
+    def __call__(self, head_out: List[torch.Tensor], labels: torch.Tensor):
+        """head_out: raw [B,A,H,W,K] per level (this rank's images); labels [T,6] with LOCAL batch indices.
+
+        Returns the dict of persistent output buffers: results [B,N,K], padded detections
+        (boxes/scores/cls/rows + cnt) and loss [1].  Buffers are reused by the next call.
+        """
+        heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
+        labels = _lib.require_cuda(labels, "labels").view(-1, 6)
+        self._prepare(heads)
+        return self._run(heads, labels)
+
+    def capture(self, head_out, labels):
+        """Capture the step for these (static) input tensors into a CUDA graph; returns a replay callable."""
+        heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
+        labels = _lib.require_cuda(labels, "labels").view(-1, 6)
+        self._prepare(heads)
+        side = torch.cuda.Stream(device=self.ctx.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):          # warm-up: sizes every cached workspace outside the capture
+                self._run(heads, labels)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.ctx.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run(heads, labels)
+        self.graph = g
+        return g.replay
+
+    def detections(self, out=None):
+        """Ragged per-image detections [k,6] = [cls, conf, x1, y1, x2, y2] (the layout utils/fit.py:96 builds). Syncs."""
+        o = out or self.out
+        cnt = o["cnt"].cpu().tolist()
+        dets = torch.cat([o["cls"].float().unsqueeze(-1), o["scores"].unsqueeze(-1), o["boxes"]], dim=2)
+        return [dets[i, :c] for i, c in enumerate(cnt)]
+
+
+def shard_labels(labels: torch.Tensor, start: int, stop: int) -> torch.Tensor:
+    """Rows of ``labels`` whose image index lies in [start, stop), re-based to local indices."""
+    keep = (labels[:, 0] >= start) & (labels[:, 0] < stop)
+    out = labels[keep].clone()
+    out[:, 0] -= start
+    return out

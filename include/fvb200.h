@@ -1,0 +1,204 @@
+/*
+ * fvb200.h -- C ABI of libfvb200.so, the B200 (sm_100a) detection hot path of fastvision.
+ *
+ * The reference (ielym/fastvision) is pure Python: it has no FFI or operator registry; its
+ * boundary for this path is a set of Python callables.  Each entry point
+ * below names the reference callable it replaces (file:line under the reference root); the
+ * Python host side in fastvision_b200/ keeps the reference's names and signatures and binds
+ * these symbols with ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  No C++ / torch types cross the ABI.
+ *   - Pointers named d_* are DEVICE pointers (current device); everything else is host memory
+ *     that is read during the call only (small geometry tables are passed to kernels by value).
+ *   - The caller owns every buffer (inputs, outputs, workspaces).  The library never allocates,
+ *     frees or retains a pointer past the call.  Tensors are contiguous fp32 unless stated.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no host sync inside.
+ *   - Return 0 on success, negative FVB_E_* otherwise; fvb_last_error() gives a thread-local
+ *     message.  Launch errors are picked up with cudaPeekAtLastError only.
+ *   - There is no CPU path: without a CUDA device every compute entry point fails.
+ */
+#ifndef FVB200_H_
+#define FVB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVB_ABI_VERSION 1
+#define FVB_MAX_LEVELS 4
+#define FVB_MAX_ANCHORS 16
+
+#define FVB_OK 0
+#define FVB_E_INVALID (-1) /* bad argument */
+#define FVB_E_CUDA (-2)    /* CUDA runtime / launch error */
+#define FVB_E_LIMIT (-3)   /* shape beyond a compiled-in limit */
+
+/* box layouts (detection/tools/IOU.py:7-25 `mode`) */
+#define FVB_BOX_XYXY 0
+#define FVB_BOX_XYWH 1
+#define FVB_BOX_WH 2
+/* IoU kinds */
+#define FVB_IOU 0
+#define FVB_GIOU 1
+#define FVB_DIOU 2
+#define FVB_CIOU 3
+/* arithmetic variant: library files vs demos/<x>/utils/iou.py */
+#define FVB_VARIANT_LIB 0
+#define FVB_VARIANT_DEMO 1
+/* decode forms: detection/models/yolov3.py:47-48 vs demos/yolov3_u/inference.py:86-89 */
+#define FVB_DECODE_V3 0
+#define FVB_DECODE_V5 1
+/* NMS front-ends */
+#define FVB_NMS_LIB 0        /* detection/tools/NMS.py:5-23, class-agnostic, rank by max_c(cls*obj), boxes xywh */
+#define FVB_NMS_DEMO 1       /* demos/yolov3_u/utils/nms.py:5-53, class-aware gap trick, rank by obj, boxes xyxy */
+#define FVB_NMS_DEMO_BATCH 2 /* demos/yolov3_u/utils/nms.py:55-98, class-aware, rank by max_c(cls*obj), boxes xywh */
+/* reductions */
+#define FVB_REDUCE_MEAN 0
+#define FVB_REDUCE_SUM 1
+
+int fvb_abi_version(void);
+const char* fvb_last_error(void);
+/* Number of kernel launches this process has enqueued through the library (bench.py: gpu_launches). */
+uint64_t fvb_launch_count(void);
+
+/* Geometry of a YOLO head stack, host memory.  Level order = concat order (stride 32,16,8). */
+typedef struct {
+  int32_t levels;   /* L <= FVB_MAX_LEVELS */
+  int32_t batch;    /* B */
+  int32_t anchors;  /* A per level <= FVB_MAX_ANCHORS */
+  int32_t channels; /* K = 5 + C */
+  int32_t height[FVB_MAX_LEVELS];
+  int32_t width[FVB_MAX_LEVELS];
+  float stride[FVB_MAX_LEVELS];
+  float anchor_w[FVB_MAX_LEVELS][FVB_MAX_ANCHORS]; /* pixels */
+  float anchor_h[FVB_MAX_LEVELS][FVB_MAX_ANCHORS];
+} fvb_yolo_geom;
+
+/* ---- K1 decode ---------------------------------------------------------------------------
+ * Replaces the decode block of Yolov3.forward, detection/models/yolov3.py:33-53 (and the demo
+ * forms, demos/yolov3_u/inference.py:86-89).  d_heads[l] is the contiguous [B,A,H_l,W_l,K] raw
+ * head tensor of level l (detection/head/yolov3head.py:63); d_results is [B,N,K] with
+ * N = A*sum(H_l*W_l), row a*H*W + y*W + x inside a level.
+ * Optional fused side outputs (either may be NULL):
+ *   d_cand_bitmap  [B, fvb_yolo_bitmap_words(geom)] u32, must be zero on entry: bit r of image b
+ *                  is set iff results[b,r,4] > conf_thr -- the candidate set of
+ *                  non_max_suppression (detection/tools/NMS.py:7-8) without a second pass;
+ *   d_conf_bce0    [fvb_yolo_decode_tiles(geom) * B] f64: per-tile sums of
+ *                  -log(1 - sigmoid(t4) + 1e-8), the zero-target part of the objectness BCE of
+ *                  Yolov3Loss (loss/yolov3_loss.py:63-64), consumed by fvb_yolov3_loss_f32.
+ * precise != 0 uses expf + IEEE division instead of ex2.approx/rcp.approx (both meet rtol 1e-5).
+ */
+int fvb_yolo_rows_per_image(const fvb_yolo_geom* geom);
+int fvb_yolo_bitmap_words(const fvb_yolo_geom* geom);
+int fvb_yolo_decode_tiles(const fvb_yolo_geom* geom); /* tiles per image */
+int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
+                        float* d_results, float conf_thr, uint32_t* d_cand_bitmap, double* d_conf_bce0,
+                        void* stream);
+
+/* ---- box conversion ------------------------------------------------------------------------
+ * detection/tools/BOX.py:4-26.  op: 0 xywh2xyxy, 1 xyxy2xywh, 2 xyxy2xywhn (needs height,width).
+ */
+int fvb_box_convert_f32(const float* d_in, int64_t n, int op, float height, float width, float* d_out,
+                        void* stream);
+
+/* ---- K2 IoU family -------------------------------------------------------------------------
+ * detection/tools/IOU.py: cal_iou :7 / GIOU :193 / DIOU :294 / CIOU :397 (element-wise, out[n])
+ * and cal_iou_batch :17 / GIOU_batch :243 / DIOU_batch :345 / CIOU_batch :442 (pairwise,
+ * out[N,M] row-major).  Bug-compatible with the torch branches.  box_mode WH takes
+ * [n,2] inputs and supports kind FVB_IOU only.
+ */
+int fvb_iou_elementwise_f32(const float* d_a, const float* d_b, int64_t n, int box_mode, int kind,
+                            int variant, float eps, float* d_out, void* stream);
+int fvb_iou_pairwise_f32(const float* d_a, int64_t n, const float* d_b, int64_t m, int box_mode, int kind,
+                         int variant, float eps, float* d_out, void* stream);
+/* loss/iou_loss.py:5-107: out[0] = reduce((1 - kind(a,b)) * w); d_weights may be NULL.
+ * d_ws: workspace of fvb_reduce_workspace_bytes(n) bytes. */
+size_t fvb_reduce_workspace_bytes(int64_t n);
+int fvb_iou_loss_f32(const float* d_pre, const float* d_true, const float* d_weights, int64_t n, int box_mode,
+                     int kind, int variant, float eps, int reduction, float* d_out, void* d_ws, void* stream);
+/* loss/classification_loss.py:36-65 BiCrossEntropyLoss.  d_pre is [rows, C]; when C > 1 d_target_idx
+ * ([rows] int64 class ids, one-hot expanded on the fly) is used, otherwise d_target_val ([rows] fp32). */
+int fvb_bce_loss_f32(const float* d_pre, int64_t rows, int classes, const int64_t* d_target_idx,
+                     const float* d_target_val, int already_sigmoid, const float* d_weights, int reduction,
+                     float* d_out, void* d_ws, void* stream);
+
+/* ---- K3 NMS --------------------------------------------------------------------------------
+ * fvb_nms_segmented_f32: the batched equivalent of torchvision.ops.nms (third party; call sites
+ * detection/tools/NMS.py:18, demos/yolov3_u/utils/nms.py:47,92, demos/faster_rcnn/models/rpn.py:198).
+ * Segment s owns boxes[seg_offsets[s] .. seg_offsets[s+1]) (xyxy) and scores; writes up to max_keep
+ * kept indices (relative to the segment start, score-descending, ties by lower index) into
+ * d_keep_idx[s*max_keep ..] and the count into d_keep_cnt[s].  iou_thr is a double because the
+ * CPU op compares the fp32 ratio against the double threshold; the kernels compare in fp32 against
+ * the largest float <= iou_thr, which decides identically.
+ */
+size_t fvb_nms_segmented_workspace_bytes(int64_t total_boxes, int segments);
+int fvb_nms_segmented_f32(const float* d_boxes, const float* d_scores, const int32_t* d_seg_offsets,
+                          int segments, int64_t total_boxes, double iou_thr, int max_keep, int32_t* d_keep_idx,
+                          int32_t* d_keep_cnt, void* d_ws, void* stream);
+
+/* fvb_yolo_nms_f32: non_max_suppression for every image of a decoded [B,N,K] tensor in one launch.
+ * Replaces detection/tools/NMS.py:5-23 (flavour LIB) and demos/yolov3_u/utils/nms.py:5-53 / :55-98.
+ * d_cand_bitmap: [B, words] candidate bitmap produced by fvb_yolo_decode_f32, or NULL to have the
+ * kernel scan results[...,4] > conf_thr itself.  If clear_bitmap != 0 the kernel zeroes the words
+ * it consumed (ready for the next decode).  Outputs are padded: d_out_boxes [B,max_det,4] xyxy (not
+ * gap-offset), d_out_scores [B,max_det], d_out_cls [B,max_det] int64, d_out_rows [B,max_det] int32
+ * (row index inside the image, or NULL), d_out_cnt [B] int32.
+ */
+size_t fvb_yolo_nms_workspace_bytes(int batch, int rows_per_image);
+int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_image, int channels, float conf_thr,
+                     double iou_thr, int max_det, int flavour, float max_wh, uint32_t* d_cand_bitmap,
+                     int clear_bitmap, float* d_out_boxes, float* d_out_scores, int64_t* d_out_cls,
+                     int32_t* d_out_rows, int32_t* d_out_cnt, void* d_ws, void* stream);
+
+/* fvb_rpn_proposals_f32: RPN.filter_proposals, demos/faster_rcnn/models/rpn.py:168-208 (+ :111-119,
+ * :160-166).  d_cls [B,H,W,A,2], d_reg [B,H,W,A,4], base_anchors (host) [A,2] (w,h) feature units.
+ * Outputs d_out_xywh [B,post_n,4], d_out_cnt [B]. */
+size_t fvb_rpn_workspace_bytes(int batch, int height, int width, int anchors);
+int fvb_rpn_proposals_f32(const float* d_cls, const float* d_reg, const float* base_anchors, int batch,
+                          int height, int width, int anchors, int pre_n, int post_n, double iou_thr,
+                          float* d_out_xywh, int32_t* d_out_cnt, void* d_ws, void* stream);
+
+/* ---- K4 target assignment + loss ---------------------------------------------------------------
+ * fvb_yolov3_loss_f32 replaces Yolov3Loss.forward, loss/yolov3_loss.py:29-72 (with build_target
+ * :75-124, CIOULoss loss/iou_loss.py:83-107, BiCrossEntropyLoss loss/classification_loss.py:36-65).
+ * d_labels [T,6] = [batch_idx, cls, xc, yc, w, h] normalised.  d_conf_bce0 = per-tile zero-target
+ * objectness sums from fvb_yolo_decode_f32 over the same heads, or NULL (the call then streams
+ * channel 4 itself).  d_partials [L*4] f64 receives per level {S_cls, S_box, S_conf, M}
+ * (what a data-parallel run all-reduces).  If d_out_loss != NULL the scalar
+ *   B * sum_l ( r_box*S_box/M + r_cls*S_cls/(M*C) + r_conf*S_conf/(B*A*H*W) )   is written to it.
+ */
+size_t fvb_yolov3_loss_workspace_bytes(const fvb_yolo_geom* geom, int64_t num_labels);
+int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                        int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                        const double* d_conf_bce0, double* d_partials, float* d_out_loss, void* d_ws,
+                        void* stream);
+/* Combine (all-reduced) partials into the scalar; batch_global/cells use the GLOBAL batch. */
+int fvb_yolov3_loss_combine_f32(const fvb_yolo_geom* geom, int64_t batch_global, const double* d_partials,
+                                float ratio_box, float ratio_conf, float ratio_cls, float* d_out_loss,
+                                void* stream);
+/* Yolov3Loss.build_target, loss/yolov3_loss.py:75-124, for one level: padded outputs of T*A rows in
+ * (t,a) row-major order with d_match[T*A] u8 flags; d_count[1] int32 = M.  Compacted (matches first,
+ * order kept) when compact != 0. */
+int fvb_yolov3_build_target_f32(const fvb_yolo_geom* geom, int level, const float* d_labels, int64_t num_labels,
+                                int compact, int64_t* d_b, int64_t* d_gxy, int64_t* d_a, int64_t* d_cls,
+                                float* d_xywh, float* d_anchor, uint8_t* d_match, int32_t* d_count,
+                                void* stream);
+
+/* ---- K5 mAP matcher ----------------------------------------------------------------------------
+ * CalculateMAP.process_one, metrics/map.py:16-83, for I images in one launch.  d_dets [sum M,6] =
+ * [cls, conf, x1,y1,x2,y2], d_det_off [I+1]; d_gts [sum N,5] = [cls, x1,y1,x2,y2], d_gt_off [I+1];
+ * thresholds (host) f64[n_thr] (<= 16).  d_correct [sum M, n_thr] u8.  d_ws: fvb_map_match_workspace_bytes.
+ */
+size_t fvb_map_match_workspace_bytes(int64_t total_dets);
+int fvb_map_match_f32(const float* d_dets, const int32_t* d_det_off, const float* d_gts, const int32_t* d_gt_off,
+                      int images, int64_t total_dets, const double* thresholds, int n_thr, uint8_t* d_correct,
+                      void* d_ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVB200_H_ */
