@@ -39,13 +39,11 @@ struct Geom {
 
 int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out);
 
-static const int kDecodeTile = 4096;  // floats per decode tile (one CTA)
 static const int kDecodeThreads = 256;
 
-inline int decode_tiles_level(const Geom& g, int l) {
-  long long seg = (long long)g.A * g.HW[l] * g.K;
-  return (int)((seg + kDecodeTile - 1) / kDecodeTile);
-}
+// The decode kernel's work unit: one warp x 32 consecutive rows of one (image, level) segment.
+// It also defines the layout of the fused objectness-BCE partials: [B][groups per image].
+inline int decode_groups_level(const Geom& g, int l) { return (g.A * g.HW[l] + 31) / 32; }
 
 // ---- device math, written to mirror torch's fp32 op order ------------------------------------------
 __device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }

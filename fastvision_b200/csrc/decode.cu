@@ -1,26 +1,26 @@
 // K1: YOLOv3 head decode, one pass over the raw head tensors (HBM-bound).
 //
 // Replaces detection/models/yolov3.py:33-53 of the reference (~30 ATen launches, ~6 full passes).
-// Layout fact the kernel is built on: inside one (image, level) segment the raw head
-// [A,H,W,K] and the decoded rows [a*H*W + y*W + x, K] are the SAME flat order, so decode is a
-// contiguous -> contiguous element-wise map with channel = e mod K and cell = e div K.
-// Each CTA owns one 4096-float tile of one segment; lanes touch consecutive floats (fully
-// coalesced 128 B per warp instruction on both sides), 16 independent loads in flight per thread.
-// Channel / cell are tracked incrementally (no per-element division); the grid coordinates
-// (x, y, anchor) are only derived for channels 0..3 via multiply-shift division.
-// Fused side outputs: the NMS candidate bitmap (conf > thr) and the zero-target objectness BCE
-// partial sums for Yolov3Loss -- both fall out of channel 4 while it is in registers.
+// Layout fact the kernel is built on: inside one (image, level) segment the raw head [A,H,W,K] and
+// the decoded rows [a*H*W + y*W + x, K] are the SAME flat order, so decode is a contiguous ->
+// contiguous map.  Work unit = one warp x 32 consecutive rows of one segment:
+//   * lanes <-> channels (c = lane + 32 j), so a warp instruction reads/writes 128 contiguous bytes,
+//     the channel of every register is known statically (no per-element index arithmetic, the
+//     xy / wh / objectness special cases cost a few selects on iteration j = 0 only) and the cell
+//     coordinates (x, y, anchor) are per-row values advanced incrementally;
+//   * rows narrower than 17 floats are packed 2 or 4 per warp iteration so lanes stay busy;
+//   * 4 rows (up to 12 independent 128-byte loads per warp) are in flight before the first use.
+// Fused side outputs fall out of channel 4 while it is in registers: every lane keeps the objectness
+// of "its" row of the group, then ONE ballot gives 32 bits of the NMS candidate bitmap and ONE
+// 32-lane pass computes the zero-target objectness BCE of Yolov3Loss for the whole group.
 #include "common.cuh"
 
 namespace fvb {
 
 struct DecodeParams {
   Geom g;
-  int tiles_level_end[FVB_MAX_LEVELS];  // cumulative tile count per image
-  int tiles_per_image;
-  unsigned long long magic_hw[FVB_MAX_LEVELS];  // floor(2^40 / HW) + 1
-  unsigned long long magic_w[FVB_MAX_LEVELS];   // floor(2^40 / W) + 1
-  int dc, dr;                                   // 256 mod K, 256 div K
+  int groups_level_end[FVB_MAX_LEVELS];  // cumulative 32-row groups per image
+  int groups_per_image;
   float* out;
   float conf_thr;
   uint32_t* bitmap;
@@ -28,102 +28,174 @@ struct DecodeParams {
   double* bce0;
 };
 
-__device__ __forceinline__ uint32_t div_magic(uint32_t n, unsigned long long m) {
-  return (uint32_t)(((unsigned long long)n * m) >> 40);
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-template <int FORM, bool PRECISE>
+constexpr float kLog2e = 1.4426950408889634f;
+
+// One 32-row group.  J = ceil(K/32) register columns per row (RPI == 1), or J = 1 with RPI rows packed
+// per warp iteration.  FULL: all 32 rows exist (every group but the last of a segment).
+template <int J, int RPI, int FORM, bool PRECISE, bool FULL>
+__device__ __forceinline__ void decode_group(const DecodeParams& p, const int l, const int b, const int grp,
+                                             const int grp_in_image) {
+  constexpr int SLOT = 32 / RPI;   // lanes per row
+  constexpr int ITERS = 32 / RPI;  // warp iterations per 32-row group
+  constexpr int UN = 4;            // iterations in flight
+  const int lane = threadIdx.x & 31;
+  const int K = p.g.K, W = p.g.W[l], H = p.g.H[l], HW = p.g.HW[l];
+  const int rows_l = p.g.A * HW;
+  const int row0 = grp * 32;
+  const int nrows = FULL ? 32 : rows_l - row0;
+  const int sub = lane / SLOT;       // row inside one iteration
+  const int c0 = lane - sub * SLOT;  // channel of register column 0
+  const int lane_off = (RPI == 1) ? lane : sub * K + c0;
+  const int K1 = RPI * K;            // floats per warp iteration
+  const float* __restrict__ rp = p.g.head[l] + ((size_t)b * rows_l + row0) * K + lane_off;
+  float* __restrict__ wp = p.out + ((size_t)b * p.g.row_off[p.g.L] + p.g.row_off[l] + row0) * K + lane_off;
+
+  bool live[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) live[j] = (RPI == 1) ? (lane + 32 * j < K) : (c0 < K);
+
+  // cell coordinates of this lane's row at iteration 0, then advanced incrementally
+  int a, y, x;
+  {
+    int rl = row0 + sub;
+    a = min(rl / HW, p.g.A - 1);
+    int yx = rl - a * HW;
+    y = yx / W;
+    x = yx - y * W;
+  }
+  const float stride = p.g.stride[l];
+  const bool is_wh = (c0 == 2) | (c0 == 3);
+  const bool is_xy = c0 < 2;
+  const float scale0 = (FORM == FVB_DECODE_V3 && is_wh) ? kLog2e : -kLog2e;
+  float anc = (c0 == 2) ? p.g.aw[l][a] : p.g.ah[l][a];
+
+  const bool fused = (p.bitmap != nullptr) | (p.bce0 != nullptr);
+  float my_t4 = 0.0f, my_conf = 0.0f;
+
+#pragma unroll 1
+  for (int it0 = 0; it0 < ITERS; it0 += UN) {
+    float v[UN][J];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const bool row_ok = FULL || ((it0 + u) * RPI + sub < nrows);
+      const float* r = rp + u * K1;
+#pragma unroll
+      for (int j = 0; j < J; ++j) v[u][j] = (row_ok && live[j]) ? r[32 * j] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int it = it0 + u;
+      const bool row_ok = FULL || (it * RPI + sub < nrows);
+      float* w = wp + u * K1;
+      float o0 = 0.0f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const float t = v[u][j];
+        float o;
+        if (j == 0) {
+          float ex, sg;
+          if (PRECISE) {
+            ex = expf((FORM == FVB_DECODE_V3 && is_wh) ? t : -t);
+            sg = 1.0f / (1.0f + ex);
+          } else {
+            ex = ex2_approx(t * scale0);
+            sg = rcp_approx(1.0f + ex);
+          }
+          const float gxy = (float)((c0 == 0) ? x : y);
+          float oxy, owh;
+          if (FORM == FVB_DECODE_V3) {
+            oxy = (sg + gxy) * stride;  // yolov3.py:47
+            owh = ex * anc;             // yolov3.py:48
+          } else {                      // demos/yolov3_u/inference.py:86-89
+            const float s2 = sg * 2.0f;
+            oxy = ((s2 - 0.5f) + gxy) * stride;
+            owh = (s2 * s2) * anc;
+          }
+          o = is_xy ? oxy : (is_wh ? owh : sg);
+          o0 = o;
+        } else {
+          if (PRECISE) o = 1.0f / (1.0f + expf(-t));
+          else o = rcp_approx(1.0f + ex2_approx(t * -kLog2e));
+        }
+        if (row_ok && live[j]) w[32 * j] = o;
+      }
+      if (fused) {
+#pragma unroll
+        for (int s = 0; s < RPI; ++s) {
+          const float tv = __shfl_sync(0xffffffffu, v[u][0], s * SLOT + 4);
+          const float ov = __shfl_sync(0xffffffffu, o0, s * SLOT + 4);
+          if (lane == it * RPI + s) {
+            my_t4 = tv;
+            my_conf = ov;
+          }
+        }
+      }
+      // advance this lane's row by RPI
+      x += RPI;
+      if (x >= W) {
+        do {
+          x -= W;
+          y += 1;
+        } while (x >= W);
+        if (y >= H) {
+          y -= H;
+          a = min(a + 1, p.g.A - 1);
+          anc = (c0 == 2) ? p.g.aw[l][a] : p.g.ah[l][a];
+        }
+      }
+    }
+    rp += UN * K1;
+    wp += UN * K1;
+  }
+
+  if (fused) {
+    const bool valid = lane < nrows;
+    if (p.bitmap != nullptr) {
+      const unsigned m = __ballot_sync(0xffffffffu, valid && my_conf > p.conf_thr);
+      const unsigned gr = (unsigned)(p.g.row_off[l] + row0);
+      const unsigned sh = gr & 31u;
+      uint32_t* wptr = p.bitmap + (size_t)b * p.bitmap_words + (gr >> 5);
+      if (lane == 0) {
+        const unsigned lo = m << sh;
+        if (lo) atomicOr(wptr, lo);
+      } else if (lane == 1 && sh) {
+        const unsigned hi = m >> (32u - sh);
+        if (hi) atomicOr(wptr + 1, hi);
+      }
+    }
+    if (p.bce0 != nullptr) {
+      const float term = valid ? bce_term(sigmoid_precise(my_t4), 0.0f) : 0.0f;
+      const double s = warp_sum((double)term);
+      if (lane == 0) p.bce0[(size_t)b * p.groups_per_image + grp_in_image] = s;
+    }
+  }
+}
+
+template <int J, int RPI, int FORM, bool PRECISE>
 __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeParams p) {
-  constexpr int U = kDecodeTile / kDecodeThreads;  // 16
   const int b = blockIdx.y;
-  int tile = blockIdx.x;
+  int grp = blockIdx.x * (kDecodeThreads / 32) + (threadIdx.x >> 5);
+  if (grp >= p.groups_per_image) return;
+  const int grp_in_image = grp;
   int l = 0;
 #pragma unroll
   for (int i = 0; i < FVB_MAX_LEVELS - 1; ++i)
-    if (i < p.g.L - 1 && tile >= p.tiles_level_end[i]) l = i + 1;
-  if (l > 0) tile -= p.tiles_level_end[l - 1];
-
-  const int K = p.g.K;
-  const uint32_t seg = (uint32_t)p.g.A * p.g.HW[l] * K;  // floats in this (image, level) segment
-  const float* __restrict__ in = p.g.head[l] + (size_t)b * seg;
-  float* __restrict__ out = p.out + ((size_t)b * p.g.row_off[p.g.L] + p.g.row_off[l]) * K;
-
-  const uint32_t e0 = (uint32_t)tile * kDecodeTile + threadIdx.x;
-  float v[U];
-#pragma unroll
-  for (int i = 0; i < U; ++i) {
-    uint32_t e = e0 + i * kDecodeThreads;
-    v[i] = e < seg ? __ldcs(in + e) : 0.0f;
-  }
-
-  uint32_t r = e0 / (uint32_t)K;  // cell (row inside the level)
-  int c = (int)(e0 - r * K);      // channel
-  const float stride = p.g.stride[l];
-  float acc = 0.0f;
-
-#pragma unroll
-  for (int i = 0; i < U; ++i) {
-    uint32_t e = e0 + i * kDecodeThreads;
-    float t = v[i];
-    bool is_wh = (c == 2) | (c == 3);
-    float o;
-    if (FORM == FVB_DECODE_V3) {
-      float ex, sg;
-      if (PRECISE) {
-        ex = expf(is_wh ? t : -t);
-        sg = 1.0f / (1.0f + ex);
-      } else {
-        ex = __expf(is_wh ? t : -t);
-        sg = __fdividef(1.0f, 1.0f + ex);
-      }
-      o = sg;
-      if (c < 4) {
-        uint32_t a = div_magic(r, p.magic_hw[l]);
-        uint32_t yx = r - a * p.g.HW[l];
-        uint32_t y = div_magic(yx, p.magic_w[l]);
-        uint32_t x = yx - y * p.g.W[l];
-        if (c == 0) o = (sg + (float)x) * stride;
-        else if (c == 1) o = (sg + (float)y) * stride;
-        else if (c == 2) o = ex * p.g.aw[l][a];
-        else o = ex * p.g.ah[l][a];
-      }
-    } else {  // FVB_DECODE_V5: demos/yolov3_u/inference.py:86-89
-      float ex = PRECISE ? expf(-t) : __expf(-t);
-      float sg = PRECISE ? 1.0f / (1.0f + ex) : __fdividef(1.0f, 1.0f + ex);
-      o = sg;
-      if (c < 4) {
-        uint32_t a = div_magic(r, p.magic_hw[l]);
-        uint32_t yx = r - a * p.g.HW[l];
-        uint32_t y = div_magic(yx, p.magic_w[l]);
-        uint32_t x = yx - y * p.g.W[l];
-        float s2 = sg * 2.0f;
-        if (c == 0) o = ((s2 - 0.5f) + (float)x) * stride;
-        else if (c == 1) o = ((s2 - 0.5f) + (float)y) * stride;
-        else if (c == 2) o = (s2 * s2) * p.g.aw[l][a];
-        else o = (s2 * s2) * p.g.ah[l][a];
-      }
-    }
-    if (c == 4 && e < seg) {
-      if (p.bitmap != nullptr && o > p.conf_thr) {
-        uint32_t row = (uint32_t)p.g.row_off[l] + r;
-        atomicOr(p.bitmap + (size_t)b * p.bitmap_words + (row >> 5), 1u << (row & 31));
-      }
-      if (p.bce0 != nullptr) acc += bce_term(sigmoid_precise(t), 0.0f);
-    }
-    if (e < seg) out[e] = o;
-    c += p.dc;
-    r += p.dr;
-    if (c >= K) {
-      c -= K;
-      r += 1;
-    }
-  }
-
-  if (p.bce0 != nullptr) {
-    __shared__ double scratch[32];
-    double s = block_sum((double)acc, scratch);
-    if (threadIdx.x == 0) p.bce0[(size_t)b * p.tiles_per_image + blockIdx.x] = s;
-  }
+    if (i < p.g.L - 1 && grp >= p.groups_level_end[i]) l = i + 1;
+  if (l > 0) grp -= p.groups_level_end[l - 1];
+  const int rows_l = p.g.A * p.g.HW[l];
+  if (rows_l - grp * 32 >= 32) decode_group<J, RPI, FORM, PRECISE, true>(p, l, b, grp, grp_in_image);
+  else decode_group<J, RPI, FORM, PRECISE, false>(p, l, b, grp, grp_in_image);
 }
 
 int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out) {
@@ -146,7 +218,7 @@ int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out) {
     out->row_off[l] = (int)rows;
     rows += (long long)g->anchors * out->HW[l];
     long long seg = (long long)g->anchors * out->HW[l] * g->channels;
-    if (seg >= (1ll << 31) || (long long)g->anchors * out->HW[l] * (long long)out->HW[l] >= (1ll << 40)) {
+    if (seg >= (1ll << 31)) {
       set_error("level %d too large for 32-bit segment indexing", l);
       return FVB_E_LIMIT;
     }
@@ -162,6 +234,19 @@ int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out) {
   }
   out->row_off[g->levels] = (int)rows;
   return FVB_OK;
+}
+
+template <int FORM, bool PRECISE>
+static void launch_decode(const DecodeParams& p, dim3 grid, cudaStream_t s) {
+  const int K = p.g.K;
+  if (K <= 8) decode_kernel<1, 4, FORM, PRECISE><<<grid, kDecodeThreads, 0, s>>>(p);
+  else if (K <= 16) decode_kernel<1, 2, FORM, PRECISE><<<grid, kDecodeThreads, 0, s>>>(p);
+  else if (K <= 32) decode_kernel<1, 1, FORM, PRECISE><<<grid, kDecodeThreads, 0, s>>>(p);
+  else if (K <= 64) decode_kernel<2, 1, FORM, PRECISE><<<grid, kDecodeThreads, 0, s>>>(p);
+  else if (K <= 96) decode_kernel<3, 1, FORM, PRECISE><<<grid, kDecodeThreads, 0, s>>>(p);
+  else if (K <= 128) decode_kernel<4, 1, FORM, PRECISE><<<grid, kDecodeThreads, 0, s>>>(p);
+  else if (K <= 192) decode_kernel<6, 1, FORM, PRECISE><<<grid, kDecodeThreads, 0, s>>>(p);
+  else decode_kernel<8, 1, FORM, PRECISE><<<grid, kDecodeThreads, 0, s>>>(p);
 }
 
 }  // namespace fvb
@@ -183,7 +268,7 @@ extern "C" int fvb_yolo_decode_tiles(const fvb_yolo_geom* geom) {
   Geom g;
   if (make_geom(geom, nullptr, &g) != FVB_OK) return -1;
   int t = 0;
-  for (int l = 0; l < g.L; ++l) t += decode_tiles_level(g, l);
+  for (int l = 0; l < g.L; ++l) t += decode_groups_level(g, l);
   return t;
 }
 
@@ -196,32 +281,30 @@ extern "C" int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const
   if (rc != FVB_OK) return rc;
   FVB_REQUIRE(form == FVB_DECODE_V3 || form == FVB_DECODE_V5, "decode: unknown form %d", form);
   FVB_REQUIRE(p.g.B <= 65535, "decode: batch %d > 65535 (grid.y)", p.g.B);
+  FVB_REQUIRE(p.g.K <= 256, "decode: channels %d > 256", p.g.K);
   for (int l = 0; l < p.g.L; ++l) FVB_REQUIRE(d_heads[l] != nullptr, "decode: head %d is NULL", l);
   if (p.g.B == 0) return FVB_OK;
   int t = 0;
   for (int l = 0; l < p.g.L; ++l) {
-    t += decode_tiles_level(p.g, l);
-    p.tiles_level_end[l] = t;
-    p.magic_hw[l] = (1ull << 40) / (unsigned long long)p.g.HW[l] + 1;
-    p.magic_w[l] = (1ull << 40) / (unsigned long long)p.g.W[l] + 1;
+    t += decode_groups_level(p.g, l);
+    p.groups_level_end[l] = t;
   }
-  for (int l = p.g.L; l < FVB_MAX_LEVELS; ++l) p.tiles_level_end[l] = t;
-  p.tiles_per_image = t;
-  p.dc = kDecodeThreads % p.g.K;
-  p.dr = kDecodeThreads / p.g.K;
+  for (int l = p.g.L; l < FVB_MAX_LEVELS; ++l) p.groups_level_end[l] = t;
+  p.groups_per_image = t;
   p.out = d_results;
   p.conf_thr = conf_thr;
   p.bitmap = d_cand_bitmap;
   p.bitmap_words = (p.g.row_off[p.g.L] + 31) / 32;
   p.bce0 = d_conf_bce0;
-  dim3 grid((unsigned)t, (unsigned)p.g.B);
+  const int wpb = kDecodeThreads / 32;
+  dim3 grid((unsigned)((t + wpb - 1) / wpb), (unsigned)p.g.B);
   cudaStream_t s = (cudaStream_t)stream;
   if (form == FVB_DECODE_V3) {
-    if (precise) decode_kernel<FVB_DECODE_V3, true><<<grid, kDecodeThreads, 0, s>>>(p);
-    else decode_kernel<FVB_DECODE_V3, false><<<grid, kDecodeThreads, 0, s>>>(p);
+    if (precise) launch_decode<FVB_DECODE_V3, true>(p, grid, s);
+    else launch_decode<FVB_DECODE_V3, false>(p, grid, s);
   } else {
-    if (precise) decode_kernel<FVB_DECODE_V5, true><<<grid, kDecodeThreads, 0, s>>>(p);
-    else decode_kernel<FVB_DECODE_V5, false><<<grid, kDecodeThreads, 0, s>>>(p);
+    if (precise) launch_decode<FVB_DECODE_V5, true>(p, grid, s);
+    else launch_decode<FVB_DECODE_V5, false>(p, grid, s);
   }
   count_launch();
   return check_launch("decode_kernel");

@@ -399,7 +399,7 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
     int t = 0;
     for (int l = 0; l < g.L; ++l) {
       fp.level_begin[l] = t;
-      t += decode_tiles_level(g, l);
+      t += decode_groups_level(g, l);
       fp.level_end[l] = t;
     }
     fp.tiles_per_image = t;

@@ -87,14 +87,14 @@ typedef struct {
  *   d_cand_bitmap  [B, fvb_yolo_bitmap_words(geom)] u32, must be zero on entry: bit r of image b
  *                  is set iff results[b,r,4] > conf_thr -- the candidate set of
  *                  non_max_suppression (detection/tools/NMS.py:7-8) without a second pass;
- *   d_conf_bce0    [fvb_yolo_decode_tiles(geom) * B] f64: per-tile sums of
+ *   d_conf_bce0    [fvb_yolo_decode_tiles(geom) * B] f64: per-work-group sums of
  *                  -log(1 - sigmoid(t4) + 1e-8), the zero-target part of the objectness BCE of
  *                  Yolov3Loss (loss/yolov3_loss.py:63-64), consumed by fvb_yolov3_loss_f32.
  * precise != 0 uses expf + IEEE division instead of ex2.approx/rcp.approx (both meet rtol 1e-5).
  */
 int fvb_yolo_rows_per_image(const fvb_yolo_geom* geom);
 int fvb_yolo_bitmap_words(const fvb_yolo_geom* geom);
-int fvb_yolo_decode_tiles(const fvb_yolo_geom* geom); /* tiles per image */
+int fvb_yolo_decode_tiles(const fvb_yolo_geom* geom); /* 32-row work groups per image = partials per image */
 int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
                         float* d_results, float conf_thr, uint32_t* d_cand_bitmap, double* d_conf_bce0,
                         void* stream);
@@ -165,7 +165,7 @@ int fvb_rpn_proposals_f32(const float* d_cls, const float* d_reg, const float* b
 /* ---- K4 target assignment + loss ---------------------------------------------------------------
  * fvb_yolov3_loss_f32 replaces Yolov3Loss.forward, loss/yolov3_loss.py:29-72 (with build_target
  * :75-124, CIOULoss loss/iou_loss.py:83-107, BiCrossEntropyLoss loss/classification_loss.py:36-65).
- * d_labels [T,6] = [batch_idx, cls, xc, yc, w, h] normalised.  d_conf_bce0 = per-tile zero-target
+ * d_labels [T,6] = [batch_idx, cls, xc, yc, w, h] normalised.  d_conf_bce0 = per-group zero-target
  * objectness sums from fvb_yolo_decode_f32 over the same heads, or NULL (the call then streams
  * channel 4 itself).  d_partials [L*4] f64 receives per level {S_cls, S_box, S_conf, M}
  * (what a data-parallel run all-reduces).  If d_out_loss != NULL the scalar
