@@ -37,7 +37,7 @@ _SIGS = {
     "fvb_yolo_rows_per_image": (C.c_int, [C.POINTER(Geom)]),
     "fvb_yolo_bitmap_words": (C.c_int, [C.POINTER(Geom)]),
     "fvb_yolo_decode_tiles": (C.c_int, [C.POINTER(Geom)]),
-    "fvb_yolo_decode_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), C.c_int, C.c_int, _P, C.c_float, _P, _P, _P]),
+    "fvb_yolo_decode_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), C.c_int, C.c_int, _P, C.c_float, _P, _P, _P, _P]),
     "fvb_box_convert_f32": (C.c_int, [_P, C.c_int64, C.c_int, C.c_float, C.c_float, _P, _P]),
     "fvb_iou_elementwise_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "fvb_iou_pairwise_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
@@ -48,7 +48,7 @@ _SIGS = {
     "fvb_nms_segmented_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_double, C.c_int, _P, _P, _P, _P]),
     "fvb_yolo_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "fvb_yolo_nms_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_int, C.c_int, C.c_float,
-                                   _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+                                   _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "fvb_rpn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fvb_rpn_proposals_f32": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_double, _P, _P, _P, _P]),

@@ -41,9 +41,10 @@ int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out);
 
 static const int kDecodeThreads = 256;
 
-// The decode kernel's work unit: one warp x 32 consecutive rows of one (image, level) segment.
-// It also defines the layout of the fused objectness-BCE partials: [B][groups per image].
-inline int decode_groups_level(const Geom& g, int l) { return (g.A * g.HW[l] + 31) / 32; }
+// The decode kernel's work unit: one warp x 32 consecutive rows of one (image, level) segment, 8 warps
+// per CTA, CTAs never straddle levels.  It also defines the layout of the fused objectness-BCE
+// partials: [B][blocks per image], blocks of an image ordered level by level.
+inline int decode_blocks_level(const Geom& g, int l) { return (g.A * g.HW[l] + 255) / 256; }
 
 // ---- device math, written to mirror torch's fp32 op order ------------------------------------------
 __device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -19,13 +19,14 @@ namespace fvb {
 
 struct DecodeParams {
   Geom g;
-  int groups_level_end[FVB_MAX_LEVELS];  // cumulative 32-row groups per image
-  int groups_per_image;
+  int blocks_level_end[FVB_MAX_LEVELS];  // cumulative CTAs (8 groups of 32 rows each) per image
+  int blocks_per_image;
   float* out;
   float conf_thr;
   uint32_t* bitmap;
   int bitmap_words;
-  double* bce0;
+  float* cand_rec;   // [B][N][8] = {row[0..3], conf, max_c(cls*conf), argmax as int bits, -}, written for candidates only
+  double* bce0;      // [blocks_per_image][B]: one zero-target objectness BCE partial per CTA
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -43,9 +44,10 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 // One 32-row group.  J = ceil(K/32) register columns per row (RPI == 1), or J = 1 with RPI rows packed
 // per warp iteration.  FULL: all 32 rows exist (every group but the last of a segment).
+// side: per-warp shared scratch [2][32] (raw objectness logit and decoded objectness of each row).
 template <int J, int RPI, int FORM, bool PRECISE, bool FULL>
 __device__ __forceinline__ void decode_group(const DecodeParams& p, const int l, const int b, const int grp,
-                                             const int grp_in_image) {
+                                             float* side, double* block_acc) {
   constexpr int SLOT = 32 / RPI;   // lanes per row
   constexpr int ITERS = 32 / RPI;  // warp iterations per 32-row group
   constexpr int UN = 4;            // iterations in flight
@@ -58,12 +60,12 @@ __device__ __forceinline__ void decode_group(const DecodeParams& p, const int l,
   const int c0 = lane - sub * SLOT;  // channel of register column 0
   const int lane_off = (RPI == 1) ? lane : sub * K + c0;
   const int K1 = RPI * K;            // floats per warp iteration
+  const size_t out_row0 = (size_t)b * p.g.row_off[p.g.L] + p.g.row_off[l] + row0;
   const float* __restrict__ rp = p.g.head[l] + ((size_t)b * rows_l + row0) * K + lane_off;
-  float* __restrict__ wp = p.out + ((size_t)b * p.g.row_off[p.g.L] + p.g.row_off[l] + row0) * K + lane_off;
+  float* __restrict__ wp = p.out + out_row0 * K + lane_off;
 
-  bool live[J];
-#pragma unroll
-  for (int j = 0; j < J; ++j) live[j] = (RPI == 1) ? (lane + 32 * j < K) : (c0 < K);
+  // RPI == 1: columns j < J-1 are always inside the row (J = ceil(K/32)); only the last one is ragged
+  const bool last_live = (RPI == 1) ? (lane + 32 * (J - 1) < K) : (c0 < K);
 
   // cell coordinates of this lane's row at iteration 0, then advanced incrementally
   int a, y, x;
@@ -79,9 +81,7 @@ __device__ __forceinline__ void decode_group(const DecodeParams& p, const int l,
   const bool is_xy = c0 < 2;
   const float scale0 = (FORM == FVB_DECODE_V3 && is_wh) ? kLog2e : -kLog2e;
   float anc = (c0 == 2) ? p.g.aw[l][a] : p.g.ah[l][a];
-
   const bool fused = (p.bitmap != nullptr) | (p.bce0 != nullptr);
-  float my_t4 = 0.0f, my_conf = 0.0f;
 
 #pragma unroll 1
   for (int it0 = 0; it0 < ITERS; it0 += UN) {
@@ -91,14 +91,16 @@ __device__ __forceinline__ void decode_group(const DecodeParams& p, const int l,
       const bool row_ok = FULL || ((it0 + u) * RPI + sub < nrows);
       const float* r = rp + u * K1;
 #pragma unroll
-      for (int j = 0; j < J; ++j) v[u][j] = (row_ok && live[j]) ? r[32 * j] : 0.0f;
+      for (int j = 0; j < J; ++j) {
+        const bool ok = row_ok && (j < J - 1 || last_live);
+        v[u][j] = ok ? r[32 * j] : 0.0f;
+      }
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int it = it0 + u;
       const bool row_ok = FULL || (it * RPI + sub < nrows);
       float* w = wp + u * K1;
-      float o0 = 0.0f;
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const float t = v[u][j];
@@ -123,23 +125,15 @@ __device__ __forceinline__ void decode_group(const DecodeParams& p, const int l,
             owh = (s2 * s2) * anc;
           }
           o = is_xy ? oxy : (is_wh ? owh : sg);
-          o0 = o;
+          if (fused && c0 == 4 && row_ok) {  // objectness of row it*RPI+sub: raw logit and decoded value
+            side[it * RPI + sub] = t;
+            side[32 + it * RPI + sub] = o;
+          }
         } else {
           if (PRECISE) o = 1.0f / (1.0f + expf(-t));
           else o = rcp_approx(1.0f + ex2_approx(t * -kLog2e));
         }
-        if (row_ok && live[j]) w[32 * j] = o;
-      }
-      if (fused) {
-#pragma unroll
-        for (int s = 0; s < RPI; ++s) {
-          const float tv = __shfl_sync(0xffffffffu, v[u][0], s * SLOT + 4);
-          const float ov = __shfl_sync(0xffffffffu, o0, s * SLOT + 4);
-          if (lane == it * RPI + s) {
-            my_t4 = tv;
-            my_conf = ov;
-          }
-        }
+        if (row_ok && (j < J - 1 || last_live)) w[32 * j] = o;
       }
       // advance this lane's row by RPI
       x += RPI;
@@ -159,43 +153,95 @@ __device__ __forceinline__ void decode_group(const DecodeParams& p, const int l,
     wp += UN * K1;
   }
 
-  if (fused) {
-    const bool valid = lane < nrows;
-    if (p.bitmap != nullptr) {
-      const unsigned m = __ballot_sync(0xffffffffu, valid && my_conf > p.conf_thr);
-      const unsigned gr = (unsigned)(p.g.row_off[l] + row0);
-      const unsigned sh = gr & 31u;
-      uint32_t* wptr = p.bitmap + (size_t)b * p.bitmap_words + (gr >> 5);
-      if (lane == 0) {
-        const unsigned lo = m << sh;
-        if (lo) atomicOr(wptr, lo);
-      } else if (lane == 1 && sh) {
-        const unsigned hi = m >> (32u - sh);
-        if (hi) atomicOr(wptr + 1, hi);
+  if (!fused) return;
+  __syncwarp();  // side[] and this warp's decoded rows are now visible to all of its lanes
+  const bool valid = lane < nrows;
+  const float my_t4 = valid ? side[lane] : 0.0f;
+  const float my_conf = valid ? side[32 + lane] : 0.0f;
+  if (p.bitmap != nullptr) {
+    unsigned m = __ballot_sync(0xffffffffu, valid && my_conf > p.conf_thr);  // NMS.py:7 on the stored value
+    const unsigned gr = (unsigned)(p.g.row_off[l] + row0);
+    const unsigned sh = gr & 31u;
+    uint32_t* wptr = p.bitmap + (size_t)b * p.bitmap_words + (gr >> 5);
+    if (lane == 0) {
+      const unsigned lo = m << sh;
+      if (lo) atomicOr(wptr, lo);
+    } else if (lane == 1 && sh) {
+      const unsigned hi = m >> (32u - sh);
+      if (hi) atomicOr(wptr + 1, hi);
+    }
+    // candidate records (~7% of rows): re-read the decoded row (L1/L2 hit), score = max_c(cls_c*conf) on the
+    // STORED fp32 values (NMS.py:13,16: first maximum on ties)
+    if (p.cand_rec != nullptr) {
+      while (m) {
+        const int rr = __ffs(m) - 1;
+        m &= m - 1;
+        const float* row = p.out + (out_row0 + rr) * K;
+        const float first = lane < K ? row[lane] : 0.0f;
+        const float conf = __shfl_sync(0xffffffffu, first, 4);
+        float best = -INFINITY;
+        int bidx = 0x7fffffff;
+        for (int ch = lane; ch < K; ch += 32) {
+          if (ch >= 5) {
+            const float pr = (ch < 32 ? first : row[ch]) * conf;
+            if (pr > best) {
+              best = pr;
+              bidx = ch - 5;
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+          if (ob > best || (ob == best && oi < bidx)) {
+            best = ob;
+            bidx = oi;
+          }
+        }
+        if (lane < 7) {
+          const float val = lane < 5 ? first : (lane == 5 ? best : __int_as_float(bidx));
+          p.cand_rec[(out_row0 + rr) * 8 + lane] = val;
+        }
       }
     }
-    if (p.bce0 != nullptr) {
-      const float term = valid ? bce_term(sigmoid_precise(my_t4), 0.0f) : 0.0f;
-      const double s = warp_sum((double)term);
-      if (lane == 0) p.bce0[(size_t)b * p.groups_per_image + grp_in_image] = s;
-    }
+  }
+  if (p.bce0 != nullptr) {
+    const float term = valid ? bce_term(sigmoid_precise(my_t4), 0.0f) : 0.0f;
+    const double s = warp_sum((double)term);
+    if (lane == 0) *block_acc = s;
   }
 }
 
+// grid.x enumerates 8-group blocks level by level (a block never straddles two levels), grid.y = image.
 template <int J, int RPI, int FORM, bool PRECISE>
 __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodeParams p) {
+  constexpr int WPB = kDecodeThreads / 32;
+  __shared__ float side[WPB][64];
+  __shared__ double acc[WPB];
   const int b = blockIdx.y;
-  int grp = blockIdx.x * (kDecodeThreads / 32) + (threadIdx.x >> 5);
-  if (grp >= p.groups_per_image) return;
-  const int grp_in_image = grp;
-  int l = 0;
+  const int warp = threadIdx.x >> 5;
+  int blk = blockIdx.x, l = 0;
 #pragma unroll
   for (int i = 0; i < FVB_MAX_LEVELS - 1; ++i)
-    if (i < p.g.L - 1 && grp >= p.groups_level_end[i]) l = i + 1;
-  if (l > 0) grp -= p.groups_level_end[l - 1];
+    if (i < p.g.L - 1 && blk >= p.blocks_level_end[i]) l = i + 1;
+  if (l > 0) blk -= p.blocks_level_end[l - 1];
+  const int grp = blk * WPB + warp;
   const int rows_l = p.g.A * p.g.HW[l];
-  if (rows_l - grp * 32 >= 32) decode_group<J, RPI, FORM, PRECISE, true>(p, l, b, grp, grp_in_image);
-  else decode_group<J, RPI, FORM, PRECISE, false>(p, l, b, grp, grp_in_image);
+  if ((threadIdx.x & 31) == 0) acc[warp] = 0.0;
+  if (grp * 32 < rows_l) {
+    if (rows_l - grp * 32 >= 32) decode_group<J, RPI, FORM, PRECISE, true>(p, l, b, grp, side[warp], &acc[warp]);
+    else decode_group<J, RPI, FORM, PRECISE, false>(p, l, b, grp, side[warp], &acc[warp]);
+  }
+  if (p.bce0 != nullptr) {  // one partial per block, summed in a fixed order
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < WPB; ++i) s += acc[i];
+      p.bce0[(size_t)blockIdx.x * p.g.B + b] = s;  // [blocks_per_image][B]: a level's partials are contiguous
+    }
+  }
 }
 
 int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out) {
@@ -268,13 +314,13 @@ extern "C" int fvb_yolo_decode_tiles(const fvb_yolo_geom* geom) {
   Geom g;
   if (make_geom(geom, nullptr, &g) != FVB_OK) return -1;
   int t = 0;
-  for (int l = 0; l < g.L; ++l) t += decode_groups_level(g, l);
+  for (int l = 0; l < g.L; ++l) t += decode_blocks_level(g, l);
   return t;
 }
 
 extern "C" int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
-                                   float* d_results, float conf_thr, uint32_t* d_cand_bitmap, double* d_conf_bce0,
-                                   void* stream) {
+                                   float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
+                                   double* d_conf_bce0, void* stream) {
   DecodeParams p;
   FVB_REQUIRE(d_heads != nullptr && d_results != nullptr, "decode: NULL head/result pointer");
   int rc = make_geom(geom, d_heads, &p.g);
@@ -286,18 +332,19 @@ extern "C" int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const
   if (p.g.B == 0) return FVB_OK;
   int t = 0;
   for (int l = 0; l < p.g.L; ++l) {
-    t += decode_groups_level(p.g, l);
-    p.groups_level_end[l] = t;
+    t += decode_blocks_level(p.g, l);
+    p.blocks_level_end[l] = t;
   }
-  for (int l = p.g.L; l < FVB_MAX_LEVELS; ++l) p.groups_level_end[l] = t;
-  p.groups_per_image = t;
+  for (int l = p.g.L; l < FVB_MAX_LEVELS; ++l) p.blocks_level_end[l] = t;
+  p.blocks_per_image = t;
   p.out = d_results;
   p.conf_thr = conf_thr;
   p.bitmap = d_cand_bitmap;
   p.bitmap_words = (p.g.row_off[p.g.L] + 31) / 32;
   p.bce0 = d_conf_bce0;
-  const int wpb = kDecodeThreads / 32;
-  dim3 grid((unsigned)((t + wpb - 1) / wpb), (unsigned)p.g.B);
+  p.cand_rec = d_cand_rec;
+  FVB_REQUIRE(d_cand_rec == nullptr || d_cand_bitmap != nullptr, "decode: candidate records need the candidate bitmap too");
+  dim3 grid((unsigned)t, (unsigned)p.g.B);
   cudaStream_t s = (cudaStream_t)stream;
   if (form == FVB_DECODE_V3) {
     if (precise) launch_decode<FVB_DECODE_V3, true>(p, grid, s);

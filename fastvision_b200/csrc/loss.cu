@@ -24,7 +24,7 @@ struct LossParams {
   Geom g;
   const float* labels;
   int T;
-  double* match_ws;  // [L*T*A][4] = {S_cls, box term, conf correction, matched}
+  double* match_ws;  // [L][blocks][4] = per-CTA sums of {S_cls, box term, conf correction, matched}
   int* flags;        // [0] labels grouped by image
 };
 
@@ -69,83 +69,91 @@ __device__ __forceinline__ TargetCell target_cell(const Geom& g, int l, const fl
 }
 
 __global__ void __launch_bounds__(kLossThreads) loss_match_kernel(const LossParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long wid = ((long long)blockIdx.x * kLossThreads + threadIdx.x) >> 5;
+  // grid.x: blocks of 8 (target, anchor) pairs, grid.y: level; one warp per (level, target, anchor)
+  __shared__ double part[kLossThreads / 32][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int TA = p.T * p.g.A;
-  if (wid >= (long long)p.g.L * TA) return;
-  const int l = (int)(wid / TA);
-  const int ta = (int)(wid - (long long)l * TA);
-  const int t = ta / p.g.A, a = ta - t * p.g.A;
-  double* out = p.match_ws + (size_t)wid * 4;
+  const int l = blockIdx.y;
+  const int ta = blockIdx.x * (kLossThreads / 32) + warp;
+  double r_cls = 0.0, r_box = 0.0, r_conf = 0.0, r_m = 0.0;
 
-  const TargetCell c = target_cell(p.g, l, p.labels + (size_t)t * 6, a);
-  if (!c.match || c.b < 0 || c.b >= p.g.B) {  // (an out-of-range batch index raises in the reference)
-    if (lane < 4) out[lane] = 0.0;
-    return;
-  }
-  const int K = p.g.K, C = K - 5;
-  const float* row = p.g.head[l] + ((((size_t)c.b * p.g.A + a) * p.g.H[l] + c.gy) * p.g.W[l] + c.gx) * K;
+  if (ta < TA) {
+    const int t = ta / p.g.A, a = ta - t * p.g.A;
+    const TargetCell c = target_cell(p.g, l, p.labels + (size_t)t * 6, a);
+    if (c.match && c.b >= 0 && c.b < p.g.B) {  // (an out-of-range batch index raises in the reference)
+      const int K = p.g.K;
+      const float* row = p.g.head[l] + ((((size_t)c.b * p.g.A + a) * p.g.H[l] + c.gy) * p.g.W[l] + c.gx) * K;
 
-  // class BCE over the matched row (:50-52), lanes over channels
-  float first = lane < K ? row[lane] : 0.0f;  // channels 0..31 (K >= 6)
-  double s_cls = 0.0;
-  for (int ch = lane; ch < K; ch += 32) {
-    float v = ch < 32 ? first : row[ch];
-    if (ch >= 5) {
-      float prob = sigmoid_precise(v);
-      float tgt = (ch - 5 == c.cls) ? 1.0f : 0.0f;
-      s_cls += (double)bce_term(prob, tgt);
-    }
-  }
-  s_cls = warp_sum(s_cls);
-  (void)C;
-
-  const float r0 = __shfl_sync(0xffffffffu, first, 0), r1 = __shfl_sync(0xffffffffu, first, 1);
-  const float r2 = __shfl_sync(0xffffffffu, first, 2), r3 = __shfl_sync(0xffffffffu, first, 3);
-  const float r4 = __shfl_sync(0xffffffffu, first, 4);
-
-  // duplicate cells: targets_conf[...] = iou (:61) keeps the LAST match in (t,a) order on CPU.
-  // This match loses iff a later target of the same image hits the same cell with the same anchor.
-  const bool grouped = p.flags[0] != 0;
-  bool loser = false;
-  for (int t2b = t + 1; t2b < p.T; t2b += 32) {
-    int t2 = t2b + lane;
-    bool hit = false;
-    int b2 = 0x7fffffff;
-    if (t2 < p.T) {
-      const float* lab2 = p.labels + (size_t)t2 * 6;
-      b2 = (int)lab2[0];
-      if (b2 == c.b) {
-        TargetCell c2 = target_cell(p.g, l, lab2, a);
-        hit = c2.match && c2.gx == c.gx && c2.gy == c.gy;
+      // class BCE over the matched row (:50-52), lanes over channels
+      const float first = lane < K ? row[lane] : 0.0f;  // channels 0..31 (K >= 6)
+      double s_cls = 0.0;
+      for (int ch = lane; ch < K; ch += 32) {
+        const float v = ch < 32 ? first : row[ch];
+        if (ch >= 5) {
+          const float prob = sigmoid_precise(v);
+          const float tgt = (ch - 5 == c.cls) ? 1.0f : 0.0f;
+          s_cls += (double)bce_term(prob, tgt);
+        }
       }
-    }
-    if (__any_sync(0xffffffffu, hit)) {
-      loser = true;
-      break;
-    }
-    // grouped labels: once a whole row of 32 is past image b nothing later can collide
-    if (grouped && __all_sync(0xffffffffu, b2 > c.b)) break;
-  }
+      s_cls = warp_sum(s_cls);
 
-  if (lane == 0) {
-    // predicted box in cell units (:54-56) vs [offset, wh] (:57), both xywh (:58,:60)
-    float px = sigmoid_precise(r0), py = sigmoid_precise(r1);
-    float pw = expf(r2) * c.aw, ph = expf(r3) * c.ah;
-    Box pb = xywh_to_xyxy(px, py, pw, ph);
-    Box tb = xywh_to_xyxy(c.offx, c.offy, c.tw, c.th);
-    const float eps = 1e-7f;
-    float ciou = iou_family<false>(pb, tb, FVB_CIOU, FVB_VARIANT_LIB, eps);
-    float iou = iou_plain<true>(pb, tb, eps);
-    double conf_corr = 0.0;
-    if (!loser) {
-      float pc = sigmoid_precise(r4);
-      conf_corr = (double)bce_term(pc, iou) - (double)bce_term(pc, 0.0f);
+      const float r0 = __shfl_sync(0xffffffffu, first, 0), r1 = __shfl_sync(0xffffffffu, first, 1);
+      const float r2 = __shfl_sync(0xffffffffu, first, 2), r3 = __shfl_sync(0xffffffffu, first, 3);
+      const float r4 = __shfl_sync(0xffffffffu, first, 4);
+
+      // duplicate cells: targets_conf[...] = iou (:61) keeps the LAST match in (t,a) order on CPU.
+      // This match loses iff a later target of the same image hits the same cell with the same anchor.
+      const bool grouped = p.flags[0] != 0;
+      bool loser = false;
+      for (int t2b = t + 1; t2b < p.T; t2b += 32) {
+        const int t2 = t2b + lane;
+        bool hit = false;
+        int b2 = 0x7fffffff;
+        if (t2 < p.T) {
+          const float* lab2 = p.labels + (size_t)t2 * 6;
+          b2 = (int)lab2[0];
+          if (b2 == c.b) {
+            const TargetCell c2 = target_cell(p.g, l, lab2, a);
+            hit = c2.match && c2.gx == c.gx && c2.gy == c.gy;
+          }
+        }
+        if (__any_sync(0xffffffffu, hit)) {
+          loser = true;
+          break;
+        }
+        // grouped labels: once a whole row of 32 is past image b nothing later can collide
+        if (grouped && __all_sync(0xffffffffu, b2 > c.b)) break;
+      }
+
+      // predicted box in cell units (:54-56) vs [offset, wh] (:57), both xywh (:58,:60)
+      const float px = sigmoid_precise(r0), py = sigmoid_precise(r1);
+      const float pw = expf(r2) * c.aw, ph = expf(r3) * c.ah;
+      const Box pb = xywh_to_xyxy(px, py, pw, ph);
+      const Box tb = xywh_to_xyxy(c.offx, c.offy, c.tw, c.th);
+      const float eps = 1e-7f;
+      const float ciou = iou_family<false>(pb, tb, FVB_CIOU, FVB_VARIANT_LIB, eps);
+      const float iou = iou_plain<true>(pb, tb, eps);
+      if (!loser) {
+        const float pc = sigmoid_precise(r4);
+        r_conf = (double)bce_term(pc, iou) - (double)bce_term(pc, 0.0f);
+      }
+      r_cls = s_cls;
+      r_box = (double)(1.0f - ciou);
+      r_m = 1.0;
     }
-    out[0] = s_cls;
-    out[1] = (double)(1.0f - ciou);
-    out[2] = conf_corr;
-    out[3] = 1.0;
+  }
+  if (lane == 0) {
+    part[warp][0] = r_cls;
+    part[warp][1] = r_box;
+    part[warp][2] = r_conf;
+    part[warp][3] = r_m;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLossThreads / 32; ++w) s += part[w][threadIdx.x];  // fixed order
+    p.match_ws[((size_t)l * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = s;
   }
 }
 
@@ -181,12 +189,10 @@ __global__ void __launch_bounds__(256) conf_stream_kernel(const StreamParams p) 
 
 struct FinalizeParams {
   Geom g;
-  int T;
+  int match_blocks;  // per-level CTA count of loss_match (0 when there are no labels)
   const double* match_ws;
-  const double* conf0;  // decode layout [B][tiles_per_image] (mode 0) or stream layout (mode 1)
-  int conf_mode;
-  int tiles_per_image;
-  int level_begin[FVB_MAX_LEVELS];  // mode 0: tile range inside an image; mode 1: partial range
+  const double* conf0;              // zero-target objectness partials, level-major (decode or conf_stream layout)
+  int level_begin[FVB_MAX_LEVELS];  // contiguous partial range of each level
   int level_end[FVB_MAX_LEVELS];
   double* partials;  // [L][4]
   float* out_loss;
@@ -207,29 +213,36 @@ __device__ __forceinline__ float combine_loss(const Geom& g, const double* parti
   return (float)(tot * (double)batch_global);                                          // :66-72
 }
 
+// sum of a contiguous double range with 4 independent loads in flight per thread (single CTA)
+__device__ __forceinline__ double strided_sum(const double* v, int n) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  const int step = blockDim.x;
+  int i = threadIdx.x;
+  for (; i + 3 * step < n; i += 4 * step) {
+    double a = v[i], b = v[i + step], c = v[i + 2 * step], d = v[i + 3 * step];
+    s0 += a; s1 += b; s2 += c; s3 += d;
+  }
+  for (; i < n; i += step) s0 += v[i];
+  return (s0 + s1) + (s2 + s3);
+}
+
 __global__ void __launch_bounds__(1024) loss_finalize_kernel(const FinalizeParams p) {
   __shared__ double scratch[32];
-  const int TA = p.T * p.g.A;
+  const int TA = p.match_blocks;
   for (int l = 0; l < p.g.L; ++l) {
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    const double* ws = p.match_ws + (size_t)l * TA * 4;
-    for (int i = threadIdx.x; i < TA; i += blockDim.x) {
-      a0 += ws[(size_t)i * 4 + 0];
-      a1 += ws[(size_t)i * 4 + 1];
-      a2 += ws[(size_t)i * 4 + 2];
-      a3 += ws[(size_t)i * 4 + 3];
+    const double2* ws = reinterpret_cast<const double2*>(p.match_ws + (size_t)l * TA * 4);
+    int i = threadIdx.x;
+    for (; i + (int)blockDim.x < TA; i += 2 * blockDim.x) {
+      double2 u0 = ws[(size_t)i * 2], u1 = ws[(size_t)i * 2 + 1];
+      double2 w0 = ws[(size_t)(i + blockDim.x) * 2], w1 = ws[(size_t)(i + blockDim.x) * 2 + 1];
+      a0 += u0.x + w0.x; a1 += u0.y + w0.y; a2 += u1.x + w1.x; a3 += u1.y + w1.y;
     }
-    double c0 = 0;
-    if (p.conf_mode == 0) {
-      int per = p.level_end[l] - p.level_begin[l];
-      long long total = (long long)per * p.g.B;
-      for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-        int b = (int)(i / per), k = (int)(i - (long long)b * per);
-        c0 += p.conf0[(size_t)b * p.tiles_per_image + p.level_begin[l] + k];
-      }
-    } else {
-      for (int i = p.level_begin[l] + threadIdx.x; i < p.level_end[l]; i += blockDim.x) c0 += p.conf0[i];
+    for (; i < TA; i += blockDim.x) {
+      double2 u0 = ws[(size_t)i * 2], u1 = ws[(size_t)i * 2 + 1];
+      a0 += u0.x; a1 += u0.y; a2 += u1.x; a3 += u1.y;
     }
+    double c0 = strided_sum(p.conf0 + p.level_begin[l], p.level_end[l] - p.level_begin[l]);
     a0 = block_sum(a0, scratch);
     a1 = block_sum(a1, scratch);
     a2 = block_sum(a2 + c0, scratch);
@@ -375,17 +388,18 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
   lp.labels = d_labels;
   lp.T = (int)num_labels;
 
+  const int wpb = kLossThreads / 32;
+  const int match_blocks = (int)(((long long)lp.T * g.A + wpb - 1) / wpb);
   if (lp.T > 0) {
     loss_prep_kernel<<<1, 1024, 0, s>>>(d_labels, lp.T, lp.flags);
-    long long warps = (long long)g.L * lp.T * g.A;
-    long long blocks = (warps * 32 + kLossThreads - 1) / kLossThreads;
-    loss_match_kernel<<<(unsigned)blocks, kLossThreads, 0, s>>>(lp);
+    dim3 grid((unsigned)match_blocks, (unsigned)g.L);
+    loss_match_kernel<<<grid, kLossThreads, 0, s>>>(lp);
     count_launch(2);
   }
 
   FinalizeParams fp;
   fp.g = g;
-  fp.T = lp.T;
+  fp.match_blocks = match_blocks;
   fp.match_ws = lp.match_ws;
   fp.partials = d_partials;
   fp.out_loss = d_out_loss;
@@ -395,14 +409,12 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
   fp.batch_global = g.B;
   if (d_conf_bce0) {
     fp.conf0 = d_conf_bce0;
-    fp.conf_mode = 0;
     int t = 0;
     for (int l = 0; l < g.L; ++l) {
       fp.level_begin[l] = t;
-      t += decode_groups_level(g, l);
+      t += decode_blocks_level(g, l) * g.B;
       fp.level_end[l] = t;
     }
-    fp.tiles_per_image = t;
   } else {
     StreamParams sp;
     sp.g = g;
@@ -419,8 +431,6 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
     conf_stream_kernel<<<t, 256, 0, s>>>(sp);
     count_launch();
     fp.conf0 = stream_parts;
-    fp.conf_mode = 1;
-    fp.tiles_per_image = 0;
   }
   loss_finalize_kernel<<<1, 1024, 0, s>>>(fp);
   count_launch();

@@ -3,11 +3,11 @@
 // Replaces the per-image Python loop of the reference (utils/fit.py:94-95) around
 // non_max_suppression (detection/tools/NMS.py:5-23; demo flavours demos/yolov3_u/utils/nms.py) and
 // the third-party torchvision.ops.nms it calls.  Phases, all inside one CTA:
-//   0  candidates: popcount/scan of the image's candidate bitmap (written by the decode kernel, or
-//      built here from results[...,4] > conf_thr) -> rows in ascending order = the reference's
-//      boolean-mask order, so "slot" order is the tie-break order of its stable sort;
-//   1  one warp per candidate: coalesced read of the decoded row, cls*conf products, warp arg-max
-//      (first maximum), xywh->xyxy, optional class gap (box + cat*max_wh in fp32);
+//   0  candidates: popcount/scan of the image's candidate bitmap -> rows in ascending order = the
+//      reference's boolean-mask order, so "slot" order is the tie-break order of its stable sort;
+//   1  one thread per candidate: load its 32-byte record {x,y,w,h,conf,max_c(cls*conf),argmax}
+//      (written by the decode kernel while the row was in registers, or by yolo_score_kernel when
+//      NMS is called on its own), xywh->xyxy, optional class gap (box + cat*max_wh in fp32);
 //   2  block radix sort of (rank desc, slot asc) keys;
 //   3  chunked greedy suppression with a kept list (nms.cuh);
 //   4  padded outputs + count; consumed bitmap words are cleared for the next step.
@@ -29,8 +29,8 @@ struct YoloNmsParams {
   float max_wh;
   int max_nms;
   uint32_t* bitmap;  // [B, words]; either caller-provided (decode) or a workspace slice
+  const float* rec;  // [B, N, 8] candidate records
   int words;
-  int build_bitmap;  // scan results[...,4] here
   int clear_bitmap;
   float* out_boxes;
   float* out_scores;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
   extern __shared__ __align__(16) unsigned char smem[];
   const NmsSmemLayout L = nms_layout(kCapS, p.max_det);
   const int b = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L.cnt);
   uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + L.warp_tot);
   float4* kbox = reinterpret_cast<float4*>(smem + L.kbox);
@@ -88,19 +88,7 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
   GreedyShared* gs = reinterpret_cast<GreedyShared*>(smem + L.gs);
   int* misc = reinterpret_cast<int*>(smem + L.misc);  // [0] n_valid
 
-  const float* res = p.results + (size_t)b * p.N * p.K;
   uint32_t* bm = p.bitmap + (size_t)b * p.words;
-
-  // ---- phase 0': build the bitmap from the objectness channel (stand-alone use) ----------------------
-  if (p.build_bitmap) {
-    for (int w0 = warp; w0 < p.words; w0 += kNmsWarps) {
-      int r = w0 * 32 + lane;
-      bool c = (r < p.N) && (res[(size_t)r * p.K + 4] > p.conf_thr);
-      unsigned m = __ballot_sync(0xffffffffu, c);
-      if (lane == 0) bm[w0] = m;
-    }
-    __syncthreads();
-  }
 
   // ---- phase 0: ordered candidate rows from the bitmap -------------------------------------------------
   const int wpt = (p.words + kNmsThreads - 1) / kNmsThreads;
@@ -151,52 +139,35 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
     return;
   }
 
-  // ---- phase 1: score / class / box per candidate (warp per candidate) ---------------------------------
+  // ---- phase 1: one thread per candidate, from its 32-byte record -----------------------------------------
+  const float4* rec4 = reinterpret_cast<const float4*>(p.rec + (size_t)b * p.N * 8);
   int valid_local = 0;
-  for (int i = warp; i < n; i += kNmsWarps) {
-    const float* row = res + (size_t)srow[i] * p.K;
-    float conf = row[4];
-    float best = -INFINITY;
-    int bidx = 0x7fffffff;
-    for (int c = 5 + lane; c < p.K; c += 32) {
-      float v = row[c] * conf;  // prediction[:, 5:] *= prediction[:, 4:5]  (NMS.py:13)
-      if (v > best) {
-        best = v;
-        bidx = c - 5;
-      }
+  for (int i = threadIdx.x; i < n; i += kNmsThreads) {
+    const int r = srow[i];
+    const float4 q0 = rec4[(size_t)r * 2], q1 = rec4[(size_t)r * 2 + 1];
+    const float conf = q1.x, best = q1.y;
+    const int bidx = __float_as_int(q1.z);
+    Box bx;
+    if (p.flavour == FVB_NMS_DEMO) {  // boxes arrive as xyxy (demos/yolov3_u/utils/nms.py:8)
+      bx.x1 = q0.x; bx.y1 = q0.y; bx.x2 = q0.z; bx.y2 = q0.w;
+    } else {
+      bx = xywh_to_xyxy(q0.x, q0.y, q0.z, q0.w);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (ov > best || (ov == best && oi < bidx)) {
-        best = ov;
-        bidx = oi;
-      }
+    const float rank = (p.flavour == FVB_NMS_DEMO) ? conf : best;
+    bool ok = true;
+    if (p.flavour == FVB_NMS_DEMO_BATCH) ok = best > p.conf_thr;  // nms.py:80 second filter on the score
+    if (p.flavour != FVB_NMS_LIB) {
+      const float gap = (float)bidx * p.max_wh;  // nms.py:44-45, fp32
+      bx.x1 += gap; bx.y1 += gap; bx.x2 += gap; bx.y2 += gap;
     }
-    if (lane == 0) {
-      float x = row[0], y = row[1], w = row[2], h = row[3];
-      Box bx;
-      if (p.flavour == FVB_NMS_DEMO) {  // boxes arrive as xyxy (demos/yolov3_u/utils/nms.py:8)
-        bx.x1 = x; bx.y1 = y; bx.x2 = w; bx.y2 = h;
-      } else {
-        bx = xywh_to_xyxy(x, y, w, h);
-      }
-      float rank = (p.flavour == FVB_NMS_DEMO) ? conf : best;
-      bool ok = true;
-      if (p.flavour == FVB_NMS_DEMO_BATCH) ok = best > p.conf_thr;  // nms.py:80 second filter on the score
-      if (p.flavour != FVB_NMS_LIB) {
-        float gap = (float)bidx * p.max_wh;  // nms.py:44-45, fp32
-        bx.x1 += gap; bx.y1 += gap; bx.x2 += gap; bx.y2 += gap;
-      }
-      sbox[i] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
-      sscore[i] = rank;
-      scat[i] = bidx;
-      uint32_t hi = ok ? desc_key(rank) : 0xffffffffu;
-      keys0[i] = ((unsigned long long)hi << 32) | (uint32_t)i;
-      valid_local += ok ? 1 : 0;
-    }
+    sbox[i] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+    sscore[i] = rank;
+    scat[i] = bidx;
+    const uint32_t hi = ok ? desc_key(rank) : 0xffffffffu;
+    keys0[i] = ((unsigned long long)hi << 32) | (uint32_t)i;
+    valid_local += ok ? 1 : 0;
   }
+  valid_local = (int)warp_sum((float)valid_local);
   if (lane == 0 && valid_local) atomicAdd(&misc[0], valid_local);
   __syncthreads();
   const int n_use = min(misc[0], p.max_nms);
@@ -209,13 +180,12 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
   for (int i = threadIdx.x; i < kept; i += kNmsThreads) {
     int slot = kslot[i];
     int r = srow[slot];
-    const float* row = res + (size_t)r * p.K;
-    float x = row[0], y = row[1], w = row[2], h = row[3];
+    const float4 q0 = rec4[(size_t)r * 2];
     Box bx;
     if (p.flavour == FVB_NMS_DEMO) {
-      bx.x1 = x; bx.y1 = y; bx.x2 = w; bx.y2 = h;
+      bx.x1 = q0.x; bx.y1 = q0.y; bx.x2 = q0.z; bx.y2 = q0.w;
     } else {
-      bx = xywh_to_xyxy(x, y, w, h);
+      bx = xywh_to_xyxy(q0.x, q0.y, q0.z, q0.w);
     }
     size_t o = (size_t)b * p.max_det + i;
     reinterpret_cast<float4*>(p.out_boxes)[o] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
@@ -224,6 +194,63 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
     if (p.out_rows) p.out_rows[o] = r;
   }
   if (threadIdx.x == 0) p.out_cnt[b] = kept;
+}
+
+// ---- stand-alone scoring: candidate bitmap + records straight from a decoded [B,N,K] tensor ------------------
+// (used when NMS is called without the fused decode outputs).  One warp per 32 consecutive rows: lanes
+// read the objectness of "their" row, one ballot gives the bitmap word (plain store: row groups are
+// word-aligned here), then the warp walks the set bits and reads each candidate row coalesced.
+struct ScoreParams {
+  const float* results;
+  int N, K;
+  float conf_thr;
+  uint32_t* bitmap;
+  int words;
+  float* rec;
+};
+
+__global__ void __launch_bounds__(256) yolo_score_kernel(const ScoreParams p) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int w0 = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w0 >= p.words) return;
+  const float* res = p.results + (size_t)b * p.N * p.K;
+  const int r = w0 * 32 + lane;
+  const bool c = (r < p.N) && (res[(size_t)r * p.K + 4] > p.conf_thr);  // NMS.py:7
+  unsigned m = __ballot_sync(0xffffffffu, c);
+  if (lane == 0) p.bitmap[(size_t)b * p.words + w0] = m;
+  while (m) {
+    const int bit = __ffs(m) - 1;
+    m &= m - 1;
+    const int row_i = w0 * 32 + bit;
+    const float* row = res + (size_t)row_i * p.K;
+    const float first = lane < p.K ? row[lane] : 0.0f;
+    const float conf = __shfl_sync(0xffffffffu, first, 4);
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    for (int ch = lane; ch < p.K; ch += 32) {
+      if (ch >= 5) {
+        const float v = (ch < 32 ? first : row[ch]) * conf;  // NMS.py:13
+        if (v > best) {
+          best = v;
+          bidx = ch - 5;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) {  // torch.max keeps the first maximum (NMS.py:16)
+        best = ob;
+        bidx = oi;
+      }
+    }
+    if (lane < 7) {
+      const float val = lane < 5 ? first : (lane == 5 ? best : __int_as_float(bidx));
+      p.rec[((size_t)b * p.N + row_i) * 8 + lane] = val;
+    }
+  }
 }
 
 // ---- segmented NMS: the torchvision.ops.nms equivalent, one CTA per segment ---------------------------------
@@ -314,14 +341,15 @@ extern "C" size_t fvb_yolo_nms_workspace_bytes(int batch, int rows_per_image) {
   o = align_up(o + bn * 4, 256);                // cat
   o = align_up(o + bn * 4, 256);                // row
   o = align_up(o + (size_t)batch * words * 4, 256);  // private bitmap (stand-alone use)
+  o = align_up(o + bn * 32, 256);                    // private candidate records (stand-alone use)
   return o + 256;
 }
 
 extern "C" int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_image, int channels, float conf_thr,
                                 double iou_thr, int max_det, int flavour, float max_wh, uint32_t* d_cand_bitmap,
-                                int clear_bitmap, float* d_out_boxes, float* d_out_scores, int64_t* d_out_cls,
+                                const float* d_cand_rec, int clear_bitmap, float* d_out_boxes, float* d_out_scores, int64_t* d_out_cls,
                                 int32_t* d_out_rows, int32_t* d_out_cnt, void* d_ws, void* stream) {
-  FVB_REQUIRE(batch >= 0 && rows_per_image >= 1 && channels >= 6, "yolo_nms: bad shape B=%d N=%d K=%d", batch, rows_per_image, channels);
+  FVB_REQUIRE(batch >= 0 && batch <= 65535 && rows_per_image >= 1 && channels >= 6, "yolo_nms: bad shape B=%d N=%d K=%d", batch, rows_per_image, channels);
   FVB_REQUIRE(max_det >= 1, "yolo_nms: max_det=%d", max_det);
   FVB_REQUIRE(flavour >= FVB_NMS_LIB && flavour <= FVB_NMS_DEMO_BATCH, "yolo_nms: unknown flavour %d", flavour);
   FVB_REQUIRE(d_results && d_out_boxes && d_out_scores && d_out_cls && d_out_cnt && d_ws, "yolo_nms: NULL pointer");
@@ -347,14 +375,30 @@ extern "C" int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_
   p.ws_score = (float*)(w + o);             o = align_up(o + bn * 4, 256);
   p.ws_cat = (int*)(w + o);                 o = align_up(o + bn * 4, 256);
   p.ws_row = (int*)(w + o);                 o = align_up(o + bn * 4, 256);
+  FVB_REQUIRE((d_cand_bitmap == nullptr) == (d_cand_rec == nullptr), "yolo_nms: pass both the candidate bitmap and the records, or neither");
+  cudaStream_t cs = (cudaStream_t)stream;
   if (d_cand_bitmap) {
     p.bitmap = d_cand_bitmap;
-    p.build_bitmap = 0;
+    p.rec = d_cand_rec;
     p.clear_bitmap = clear_bitmap;
+    FVB_REQUIRE(((uintptr_t)d_cand_rec & 15) == 0, "yolo_nms: candidate records must be 16-byte aligned");
   } else {
     p.bitmap = (uint32_t*)(w + o);
-    p.build_bitmap = 1;
+    o = align_up(o + (size_t)batch * p.words * 4, 256);
+    float* rec = (float*)(w + o);
+    p.rec = rec;
     p.clear_bitmap = 0;
+    ScoreParams sp;
+    sp.results = d_results;
+    sp.N = rows_per_image;
+    sp.K = channels;
+    sp.conf_thr = conf_thr;
+    sp.bitmap = p.bitmap;
+    sp.words = p.words;
+    sp.rec = rec;
+    dim3 grid((unsigned)((p.words + 7) / 8), (unsigned)batch);
+    yolo_score_kernel<<<grid, 256, 0, cs>>>(sp);
+    count_launch();
   }
   p.out_boxes = d_out_boxes;
   p.out_scores = d_out_scores;
@@ -364,7 +408,7 @@ extern "C" int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_
   NmsSmemLayout L = nms_layout(kCapS, max_det);
   int rc = ensure_smem((const void*)yolo_nms_kernel, L.total, "yolo_nms");
   if (rc != FVB_OK) return rc;
-  yolo_nms_kernel<<<batch, kNmsThreads, L.total, (cudaStream_t)stream>>>(p);
+  yolo_nms_kernel<<<batch, kNmsThreads, L.total, cs>>>(p);
   count_launch();
   return check_launch("yolo_nms_kernel");
 }

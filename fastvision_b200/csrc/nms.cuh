@@ -19,12 +19,22 @@ __device__ __forceinline__ uint32_t desc_key(float s) {
 }
 
 // torchvision.ops.nms arithmetic: strict >, IEEE divide, NaN never suppresses.
+// The decision is exactly `inter / ((area_a + area_b) - inter) > thr` in fp32, evaluated lazily:
+//   * inter == 0 (the common, disjoint case): the ratio is +-0 or NaN, never > thr for thr >= 0 -- no divide
+//     (a zero numerator also sends the IEEE-division sequence down its slow path);
+//   * otherwise an approximate ratio (rcp.approx, a few ulp) decides unless it lies within 1e-5 (relative)
+//     of the threshold, and only then is the exact IEEE division evaluated.
 __device__ __forceinline__ bool nms_overlap(const float4& a, float area_a, const float4& b, float area_b, float thr) {
-  float w = fmaxf(0.0f, fminf(a.z, b.z) - fmaxf(a.x, b.x));
-  float h = fmaxf(0.0f, fminf(a.w, b.w) - fmaxf(a.y, b.y));
-  float inter = w * h;
-  float ovr = inter / ((area_a + area_b) - inter);
-  return ovr > thr;
+  const float w = fmaxf(0.0f, fminf(a.z, b.z) - fmaxf(a.x, b.x));
+  const float h = fmaxf(0.0f, fminf(a.w, b.w) - fmaxf(a.y, b.y));
+  const float inter = w * h;
+  if (thr >= 0.0f && !(inter > 0.0f)) return false;
+  const float uni = (area_a + area_b) - inter;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(uni));
+  const float q = inter * r;
+  if (fabsf(q - thr) > 1e-5f * fmaxf(fabsf(thr), 1e-30f) && fabsf(q) < 1e30f && uni > 1e-30f && uni < 1e30f) return q > thr;
+  return inter / uni > thr;
 }
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_tot /*[kNmsWarps+1]*/) {

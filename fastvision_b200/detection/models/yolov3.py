@@ -36,11 +36,18 @@ class DecodeContext:
         self.key = (self.batch, self.num_anchors, self.k, tuple(self.heights), tuple(self.widths), self.device)
         self._bitmap = None
         self._bce0 = None
+        self._rec = None
 
     def bitmap(self):
         if self._bitmap is None:  # zero once; the NMS kernel clears what it consumes
             self._bitmap = torch.zeros(self.batch, self.words, dtype=torch.int32, device=self.device)
         return self._bitmap
+
+    def records(self):
+        """[B,N,8] NMS candidate records (32 B per row; only candidate rows are ever written)."""
+        if self._rec is None:
+            self._rec = torch.empty(self.batch, self.rows, 8, dtype=torch.float32, device=self.device)
+        return self._rec
 
     def bce0(self):
         if self._bce0 is None:
@@ -52,8 +59,9 @@ def yolov3_decode(head_out, anchors_per_level, strides, form="v3", precise=False
                   conf_thres=None, want_bce0=False):
     """Decode raw heads (list of [B,A,H,W,K]) into ``results`` [B,N,K]  (yolov3.py:36-51).
 
-    With ``conf_thres`` the kernel also fills ``ctx.bitmap()`` (NMS candidates); with ``want_bce0`` it
-    fills ``ctx.bce0()`` (zero-target objectness BCE partials for Yolov3Loss).
+    With ``conf_thres`` the kernel also fills ``ctx.bitmap()`` / ``ctx.records()`` (NMS candidates and their
+    score / class / box records); with ``want_bce0`` it fills ``ctx.bce0()`` (zero-target objectness BCE
+    partials for Yolov3Loss).
     """
     heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
     if ctx is None:
@@ -62,11 +70,13 @@ def yolov3_decode(head_out, anchors_per_level, strides, form="v3", precise=False
         out = torch.empty(ctx.batch, ctx.rows, ctx.k, dtype=torch.float32, device=ctx.device)
     lib = _lib.load()
     bitmap = ctx.bitmap() if conf_thres is not None else None
+    rec = ctx.records() if conf_thres is not None else None
     bce0 = ctx.bce0() if want_bce0 else None
     with torch.cuda.device(ctx.device):
         _lib.check(lib.fvb_yolo_decode_f32(ctx.geom, _lib.head_ptrs(heads), _lib.DECODE_FORMS[form], 1 if precise else 0,
                                            _lib.dptr(out), float(conf_thres if conf_thres is not None else 0.0),
-                                           _lib.dptr(bitmap), _lib.dptr(bce0), _lib.stream()), "yolo_decode")
+                                           _lib.dptr(bitmap), _lib.dptr(rec), _lib.dptr(bce0), _lib.stream()),
+                   "yolo_decode")
     return out
 
 

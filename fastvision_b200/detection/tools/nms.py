@@ -11,11 +11,13 @@ from ... import _lib
 
 
 def non_max_suppression_batched(results, conf_thres=0.25, iou_thres=0.45, max_det=300, flavour="lib",
-                                cand_bitmap=None, clear_bitmap=True, max_wh=4096.0, want_rows=False, out=None):
+                                cand_bitmap=None, cand_records=None, clear_bitmap=True, max_wh=4096.0,
+                                want_rows=False, out=None):
     """results [B,N,K] decoded -> (boxes[B,max_det,4] xyxy, scores[B,max_det], cls[B,max_det] i64, cnt[B] i32[, rows]).
 
-    Entries past cnt[b] are undefined.  ``cand_bitmap`` is the [B, ceil(N/32)] int32 bitmap written by the
-    decode kernel for the same ``conf_thres`` (saves the pass over the objectness channel).
+    Entries past cnt[b] are undefined.  ``cand_bitmap`` / ``cand_records`` are the [B, ceil(N/32)] int32 bitmap
+    and [B,N,8] records written by the decode kernel for the same ``conf_thres`` (``DecodeContext.bitmap()`` /
+    ``.records()``); without them one extra scoring launch derives both from ``results``.
     """
     results = _lib.require_cuda(results, "results")
     if results.dim() != 3:
@@ -35,7 +37,7 @@ def non_max_suppression_batched(results, conf_thres=0.25, iou_thres=0.45, max_de
     with torch.cuda.device(dev):
         _lib.check(lib.fvb_yolo_nms_f32(_lib.dptr(results), b, n, k, float(conf_thres), float(iou_thres), int(max_det),
                                         _lib.NMS_FLAVOURS[flavour], float(max_wh), _lib.dptr(cand_bitmap),
-                                        1 if clear_bitmap else 0, _lib.dptr(boxes), _lib.dptr(scores), _lib.dptr(cls),
+                                        _lib.dptr(cand_records), 1 if clear_bitmap else 0, _lib.dptr(boxes), _lib.dptr(scores), _lib.dptr(cls),
                                         _lib.dptr(rows), _lib.dptr(cnt), _lib.dptr(ws), _lib.stream()), "yolo_nms")
     if want_rows:
         return boxes, scores, cls, cnt, rows

@@ -57,6 +57,7 @@ class ValStep:
             "partials": torch.empty(ctx.geom.levels, 4, dtype=torch.float64, device=dev),
         }
         ctx.bitmap()
+        ctx.records()
         ctx.bce0()
         self.graph = None
 
@@ -69,7 +70,7 @@ class ValStep:
         yolov3_decode(heads, self.anchors_per_level, self.strides, precise=self.precise, ctx=ctx, out=o["results"],
                       conf_thres=self.conf_thres, want_bce0=True)
         non_max_suppression_batched(o["results"], self.conf_thres, self.iou_thres, self.max_det, self.nms_flavour,
-                                    cand_bitmap=ctx.bitmap(), clear_bitmap=True,
+                                    cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=True,
                                     out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]))
         if self._distributed():
             self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])

@@ -87,17 +87,21 @@ typedef struct {
  *   d_cand_bitmap  [B, fvb_yolo_bitmap_words(geom)] u32, must be zero on entry: bit r of image b
  *                  is set iff results[b,r,4] > conf_thr -- the candidate set of
  *                  non_max_suppression (detection/tools/NMS.py:7-8) without a second pass;
- *   d_conf_bce0    [fvb_yolo_decode_tiles(geom) * B] f64: per-work-group sums of
+ *   d_cand_rec     [B, N, 8] f32 (needs d_cand_bitmap): for every candidate row r the record
+ *                  {results[b,r,0..3], conf, max_c(cls_c*conf), argmax_c as int bits, unused} -- what
+ *                  NMS.py:13-16 computes per candidate, produced while the row is in registers so the
+ *                  NMS kernel never re-reads the 4*K-byte rows; non-candidate records are not written;
+ *   d_conf_bce0    [fvb_yolo_decode_tiles(geom), B] f64: per-CTA sums (CTAs of an image ordered by level) of
  *                  -log(1 - sigmoid(t4) + 1e-8), the zero-target part of the objectness BCE of
  *                  Yolov3Loss (loss/yolov3_loss.py:63-64), consumed by fvb_yolov3_loss_f32.
  * precise != 0 uses expf + IEEE division instead of ex2.approx/rcp.approx (both meet rtol 1e-5).
  */
 int fvb_yolo_rows_per_image(const fvb_yolo_geom* geom);
 int fvb_yolo_bitmap_words(const fvb_yolo_geom* geom);
-int fvb_yolo_decode_tiles(const fvb_yolo_geom* geom); /* 32-row work groups per image = partials per image */
+int fvb_yolo_decode_tiles(const fvb_yolo_geom* geom); /* decode CTAs per image = objectness partials per image */
 int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
-                        float* d_results, float conf_thr, uint32_t* d_cand_bitmap, double* d_conf_bce0,
-                        void* stream);
+                        float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
+                        double* d_conf_bce0, void* stream);
 
 /* ---- box conversion ------------------------------------------------------------------------
  * detection/tools/BOX.py:4-26.  op: 0 xywh2xyxy, 1 xyxy2xywh, 2 xyxy2xywhn (needs height,width).
@@ -142,8 +146,9 @@ int fvb_nms_segmented_f32(const float* d_boxes, const float* d_scores, const int
 
 /* fvb_yolo_nms_f32: non_max_suppression for every image of a decoded [B,N,K] tensor in one launch.
  * Replaces detection/tools/NMS.py:5-23 (flavour LIB) and demos/yolov3_u/utils/nms.py:5-53 / :55-98.
- * d_cand_bitmap: [B, words] candidate bitmap produced by fvb_yolo_decode_f32, or NULL to have the
- * kernel scan results[...,4] > conf_thr itself.  If clear_bitmap != 0 the kernel zeroes the words
+ * d_cand_bitmap + d_cand_rec: the candidate bitmap [B, words] and records [B,N,8] produced by
+ * fvb_yolo_decode_f32 for the same conf_thr, or both NULL to have a scoring kernel build them from
+ * results (one extra launch that reads the objectness channel and the candidate rows).  If clear_bitmap != 0 the kernel zeroes the words
  * it consumed (ready for the next decode).  Outputs are padded: d_out_boxes [B,max_det,4] xyxy (not
  * gap-offset), d_out_scores [B,max_det], d_out_cls [B,max_det] int64, d_out_rows [B,max_det] int32
  * (row index inside the image, or NULL), d_out_cnt [B] int32.
@@ -151,7 +156,7 @@ int fvb_nms_segmented_f32(const float* d_boxes, const float* d_scores, const int
 size_t fvb_yolo_nms_workspace_bytes(int batch, int rows_per_image);
 int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_image, int channels, float conf_thr,
                      double iou_thr, int max_det, int flavour, float max_wh, uint32_t* d_cand_bitmap,
-                     int clear_bitmap, float* d_out_boxes, float* d_out_scores, int64_t* d_out_cls,
+                     const float* d_cand_rec, int clear_bitmap, float* d_out_boxes, float* d_out_scores, int64_t* d_out_cls,
                      int32_t* d_out_rows, int32_t* d_out_cnt, void* d_ws, void* stream);
 
 /* fvb_rpn_proposals_f32: RPN.filter_proposals, demos/faster_rcnn/models/rpn.py:168-208 (+ :111-119,

@@ -72,6 +72,17 @@ def test_decode_fused_side_outputs():
     words = ctx.bitmap().cpu().numpy().view(np.uint32)
     bits = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(batch, -1)[:, :ctx.rows].astype(bool)
     assert np.array_equal(bits, mask)
+    # candidate records: {row[0:5], max_c(cls*conf), argmax} for every candidate row, computed on the stored values
+    rec = ctx.records().cpu()
+    res_c = res.cpu()
+    for b in range(batch):
+        rows = np.nonzero(mask[b])[0]
+        cand = res_c[b, rows]
+        prod = cand[:, 5:] * cand[:, 4:5]
+        best, arg = prod.max(1)
+        assert torch.equal(rec[b, rows, :5], cand[:, :5])
+        assert torch.equal(rec[b, rows, 5], best)
+        assert np.array_equal(rec[b, rows, 6].numpy().view(np.int32), arg.numpy().astype(np.int32))
     # zero-target objectness BCE: sum of the partials == oracle sum over all cells
     want = 0.0
     for h in heads:
@@ -206,7 +217,7 @@ def test_nms_batched_config1_exact_on_same_decoded_tensor():
     heads = [h.cuda() for h in synth.make_heads(cfg, batch, labels, g)]
     ctx = DecodeContext(heads, cfg.anchors_levels(), cfg.strides)
     res = yolov3_decode(heads, cfg.anchors_levels(), cfg.strides, ctx=ctx, conf_thres=0.25)
-    boxes, scores, cls, cnt, rows = ft.non_max_suppression_batched(res, 0.25, 0.45, 300, cand_bitmap=ctx.bitmap(), want_rows=True)
+    boxes, scores, cls, cnt, rows = ft.non_max_suppression_batched(res, 0.25, 0.45, 300, cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), want_rows=True)
     assert int(ctx.bitmap().abs().sum()) == 0                # consumed words are cleared for the next step
     res_cpu = res.cpu()
     for i in range(batch):

@@ -65,7 +65,7 @@ def main():
     yolov3_decode(dh, anc, st, ctx=ctx, out=res, conf_thres=0.25, want_bce0=True)
     cand = (res[..., 4] > 0.25).sum(1)
     print("candidates/img mean %.1f max %d" % (cand.float().mean().item(), cand.max().item()))
-    rep("nms_bitmap", lambda: non_max_suppression_batched(res, 0.25, 0.45, 300, cand_bitmap=ctx.bitmap(), clear_bitmap=False))
+    rep("nms_bitmap", lambda: non_max_suppression_batched(res, 0.25, 0.45, 300, cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=False))
     rep("nms_standalone", lambda: non_max_suppression_batched(res, 0.25, 0.45, 300))
 
     class M:
