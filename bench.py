@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- images/s of the fastvision detection hot path (decode + NMS + loss) on N B200s.
+
+Contract (see the task brief / BASELINE.json):
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+For N > 1 it is launched under torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+
+A "step" is one pass of the hot path over one batch of synthetic head tensors: YOLOv3 decode of the three
+raw head levels, confidence filter + NMS for every image, and Yolov3Loss (CIoU box + objectness/class BCE).
+Workload at N=1 = BASELINE.json configs[1]: YOLOv3-416, COCO shape (80 classes, 3x3 anchors), batch 256.
+Under N ranks every rank owns 256 images (weak scaling); the loss partial sums are all-reduced (96 bytes).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fastvision_b200 import synth  # noqa: E402
+
+METRIC = "images/sec YOLOv3-416 decode+NMS+loss"
+UNIT = "images/s"
+CONFIG_ID = 2
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def workload(cfg, batch, rank):
+    g = synth.make_generator(CONFIG_ID, rank)
+    labels = synth.make_labels(cfg, batch, g)
+    heads = synth.make_heads(cfg, batch, labels, g)
+    return labels, heads
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU reference leg
+def cpu_reference_pass(heads, labels, cfg, nms_backend):
+    """One pass of the reference's CPU path on a batch: decode -> loss -> per-image NMS loop (utils/fit.py:86-95)."""
+    import oracle  # test infrastructure; allowed here as the cpu_baseline / --impl reference leg only
+    anc, st = cfg.anchors_levels(), cfg.strides
+    res = oracle.decode.decode(heads, anc, st)
+    loss = oracle.loss.yolov3_loss(heads, labels, anc, st)
+    kept = 0
+    for i in range(res.size(0)):
+        s, c, b = oracle.nms.nms_lib(res[i], 0.25, 0.45, 300, backend=nms_backend)
+        kept += s.size(0)
+    return float(loss), kept
+
+
+def pick_nms_backend():
+    try:
+        import torchvision  # noqa: F401  the op the reference itself calls (detection/tools/NMS.py:18), CPU build
+        return "torchvision"
+    except Exception:
+        return "numpy"
+
+
+def time_cpu_reference(cfg, sample_batch, rank, budget_s, min_reps, warm):
+    labels, heads = workload(cfg, sample_batch, rank)
+    backend = pick_nms_backend()
+    for _ in range(warm):
+        cpu_reference_pass(heads, labels, cfg, backend)
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < min_reps or (time.perf_counter() - t_start) < budget_s:
+        t0 = time.perf_counter()
+        cpu_reference_pass(heads, labels, cfg, backend)
+        times.append(time.perf_counter() - t0)
+        if len(times) >= 200:
+            break
+    med = statistics.median(times)
+    return sample_batch / med, med, len(times), backend
+
+
+def run_reference(args, cfg):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = args.cpu_sample
+    labels, heads = workload(cfg, sample, 0)
+    backend = pick_nms_backend()
+    for _ in range(max(args.warmup, 1) if args.warmup < 3 else 3):
+        cpu_reference_pass(heads, labels, cfg, backend)
+    steps = max(1, min(args.steps, 40))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_pass(heads, labels, cfg, backend)
+    dt = time.perf_counter() - t0
+    value = sample * steps / dt
+    sample_desc = ("%d-image slice of the %s batch (same generator and seed), decode -> Yolov3Loss -> per-image "
+                   "non_max_suppression loop, oracle port with NMS backend '%s'" % (sample, cfg.name, backend))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "YOLOv3-416 COCO-shape (80 cls, 3x3 anchors) decode+CIoU loss+NMS, batch 256 per GPU",
+                   "step_sample_images": sample, "timed_on": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ CUDA leg
+def run_cuda(args, cfg):
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference)")
+    from fastvision_b200 import _lib
+    from fastvision_b200.pipeline import ValStep
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    batch = args.batch
+    labels, heads = workload(cfg, batch, rank)
+    host_heads = [h.pin_memory() for h in heads]
+    host_labels = labels.pin_memory()
+    dh = [h.to(dev, non_blocking=True) for h in host_heads]
+    dl = host_labels.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    step = ValStep(cfg.anchors_levels(), cfg.strides, batch_global=batch * world)
+    lib = _lib.load()
+    n0 = lib.fvb_launch_count()
+    step(dh, dl)
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.fvb_launch_count() - n0)
+    decode_fn, tail_replay = step.capture(dh, dl, split_decode=True)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: K steps, inputs resident in HBM; decode bracketed by events on its own stream ----
+    for _ in range(max(args.warmup, 3)):
+        decode_fn()
+        tail_replay()
+    barrier()
+    k = args.steps
+    ev_d0 = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
+    ev_d1 = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_begin.record()
+        for i in range(k):
+            ev_d0[i].record()
+            decode_fn()
+            ev_d1[i].record()
+            tail_replay()
+        t_end.record()
+        barrier()
+    total_ms = t_begin.elapsed_time(t_end)
+    decode_ms = [a.elapsed_time(b) for a, b in zip(ev_d0, ev_d1)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = batch * world * k / (total_ms_max * 1e-3)
+
+    # ---- e2e: host buffers -> public API -> host results, copies inside the timed region --------------------
+    out = step.out
+    h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    h_boxes = torch.empty_like(out["boxes"], device="cpu").pin_memory()
+    h_scores = torch.empty_like(out["scores"], device="cpu").pin_memory()
+    h_cls = torch.empty_like(out["cls"], device="cpu").pin_memory()
+    h_cnt = torch.empty_like(out["cnt"], device="cpu").pin_memory()
+    h2d = sum(h.numel() * 4 for h in host_heads) + host_labels.numel() * 4
+    d2h = 4 + h_boxes.numel() * 4 + h_scores.numel() * 4 + h_cls.numel() * 8 + h_cnt.numel() * 4
+
+    def e2e_step():
+        for dst, src in zip(dh, host_heads):
+            dst.copy_(src, non_blocking=True)
+        dl.copy_(host_labels, non_blocking=True)
+        o = step(dh, dl)                      # the public API call (eager, 5 kernel launches)
+        h_loss.copy_(o["loss"], non_blocking=True)
+        h_boxes.copy_(o["boxes"], non_blocking=True)
+        h_scores.copy_(o["scores"], non_blocking=True)
+        h_cls.copy_(o["cls"], non_blocking=True)
+        h_cnt.copy_(o["cnt"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the loss / detections every step
+        return float(h_loss[0])
+
+    ke = max(3, min(args.e2e_steps, k))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = batch * world * ke / float(te.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        rows = step.ctx.rows
+        alg_bytes = 2 * batch * rows * step.ctx.k * 4          # one read of the heads + one write of results
+        dec_avg = sum(decode_ms) / len(decode_ms)
+        achieved = alg_bytes / (dec_avg * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "decode_traffic_bytes.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms_max / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "YOLOv3-416 COCO-shape (80 cls, 3x3 anchors) decode+CIoU loss+NMS, batch 256 per GPU "
+                                   "(BASELINE.json configs[1])",
+                       "batch_per_gpu": batch, "global_batch": batch * world, "rows_per_image": rows, "channels": step.ctx.k,
+                       "conf_thres": 0.25, "iou_thres": 0.45, "max_det": 300, "loss_ratios": [0.05, 1.0, 0.5],
+                       "labels": int(labels.size(0)), "parallelism": "per-image sharding, dp%d" % world,
+                       "l2": "inputs (%.0f MB per step) larger than the 126 MB L2; no flush needed" % (alg_bytes / 2e6),
+                       "step_launch": "decode launched eagerly between CUDA events, NMS + loss branches replayed as a CUDA graph"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": ke, "note": "pinned host heads+labels copied H2D, ValStep public call, loss + padded detections copied D2H, every step"},
+            "gpu_launches": launches_per_step * k,
+            "roofline": {"bound": "hbm", "kernel": "fvb::decode_kernel (decode + candidate bitmap/records + objectness-BCE partials)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dec_avg, "peak_source": peak_src,
+                         "step_achieved": alg_bytes * world / (total_ms_max / k * 1e-3) / 1e9 / world,
+                         "step_frac": alg_bytes / (total_ms_max / k * 1e-3) / 1e9 / peak},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            torch.set_num_threads(os.cpu_count() or 1)
+            v, med, reps, backend = time_cpu_reference(cfg, args.cpu_sample, 0, args.cpu_budget, 3, 1)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                "sample": "%d-image slice of the same workload (same generator/seed), %d passes, median %.3f s/pass; oracle port "
+                          "(torch-CPU restatement of the reference, NMS backend '%s')" % (args.cpu_sample, reps, med, backend)}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU (BASELINE configs[1]: 256)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-sample", type=int, default=16, help="images in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline timing")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = synth.COCO416
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_cuda(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

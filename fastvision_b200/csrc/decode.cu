@@ -177,30 +177,29 @@ __device__ __forceinline__ void decode_group(const DecodeParams& p, const int l,
         const int rr = __ffs(m) - 1;
         m &= m - 1;
         const float* row = p.out + (out_row0 + rr) * K;
-        const float first = lane < K ? row[lane] : 0.0f;
-        const float conf = __shfl_sync(0xffffffffu, first, 4);
-        float best = -INFINITY;
+        constexpr int JR = (RPI == 1) ? J : 1;  // K <= 32 when rows are packed
+        float o[JR];
+#pragma unroll
+        for (int j = 0; j < JR; ++j) o[j] = (lane + 32 * j < K) ? row[lane + 32 * j] : 0.0f;
+        const float conf = __shfl_sync(0xffffffffu, o[0], 4);
+        // products of two sigmoids are >= +0, so their bit patterns order like unsigned integers
+        unsigned best = 0u;
         int bidx = 0x7fffffff;
-        for (int ch = lane; ch < K; ch += 32) {
-          if (ch >= 5) {
-            const float pr = (ch < 32 ? first : row[ch]) * conf;
-            if (pr > best) {
+#pragma unroll
+        for (int j = 0; j < JR; ++j) {
+          const int ch = lane + 32 * j;
+          if (ch >= 5 && ch < K) {
+            const unsigned pr = __float_as_uint(o[j] * conf);
+            if (bidx == 0x7fffffff || pr > best) {  // strict >: the first maximum wins inside the lane
               best = pr;
               bidx = ch - 5;
             }
           }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-          if (ob > best || (ob == best && oi < bidx)) {
-            best = ob;
-            bidx = oi;
-          }
-        }
+        const unsigned wbest = __reduce_max_sync(0xffffffffu, best);
+        const int widx = __reduce_min_sync(0xffffffffu, (best == wbest) ? bidx : 0x7fffffff);
         if (lane < 7) {
-          const float val = lane < 5 ? first : (lane == 5 ? best : __int_as_float(bidx));
+          const float val = lane < 5 ? o[0] : (lane == 5 ? __uint_as_float(wbest) : __int_as_float(widx));
           p.cand_rec[(out_row0 + rr) * 8 + lane] = val;
         }
       }
@@ -219,6 +218,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodePara
   constexpr int WPB = kDecodeThreads / 32;
   __shared__ float side[WPB][64];
   __shared__ double acc[WPB];
+  __shared__ unsigned arrived;
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5;
   int blk = blockIdx.x, l = 0;
@@ -229,16 +229,23 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_kernel(const DecodePara
   const int grp = blk * WPB + warp;
   const int rows_l = p.g.A * p.g.HW[l];
   if ((threadIdx.x & 31) == 0) acc[warp] = 0.0;
+  if (p.bce0 != nullptr) {
+    if (threadIdx.x == 0) arrived = 0u;
+    __syncthreads();  // before any work: cheap, nobody waits on a slow warp here
+  }
   if (grp * 32 < rows_l) {
     if (rows_l - grp * 32 >= 32) decode_group<J, RPI, FORM, PRECISE, true>(p, l, b, grp, side[warp], &acc[warp]);
     else decode_group<J, RPI, FORM, PRECISE, false>(p, l, b, grp, side[warp], &acc[warp]);
   }
-  if (p.bce0 != nullptr) {  // one partial per block, summed in a fixed order
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  if (p.bce0 != nullptr && (threadIdx.x & 31) == 0) {
+    // one partial per block, summed in a fixed order by whichever warp finishes last (no barrier: warps
+    // that are done must not hold back the CTA's slots while a slow warp still streams)
+    __threadfence_block();
+    if (atomicAdd(&arrived, 1u) == WPB - 1) {
+      __threadfence_block();
       double s = 0.0;
 #pragma unroll
-      for (int i = 0; i < WPB; ++i) s += acc[i];
+      for (int i = 0; i < WPB; ++i) s += ((volatile double*)acc)[i];
       p.bce0[(size_t)blockIdx.x * p.g.B + b] = s;  // [blocks_per_image][B]: a level's partials are contiguous
     }
   }

@@ -22,18 +22,20 @@ __device__ __forceinline__ uint32_t desc_key(float s) {
 // The decision is exactly `inter / ((area_a + area_b) - inter) > thr` in fp32, evaluated lazily:
 //   * inter == 0 (the common, disjoint case): the ratio is +-0 or NaN, never > thr for thr >= 0 -- no divide
 //     (a zero numerator also sends the IEEE-division sequence down its slow path);
-//   * otherwise an approximate ratio (rcp.approx, a few ulp) decides unless it lies within 1e-5 (relative)
-//     of the threshold, and only then is the exact IEEE division evaluated.
+//   * otherwise compare inter against thr*union: unless the two are within 1e-5 (relative) of each
+//     other that product test has the same outcome as the rounded quotient test, and only in the
+//     narrow band is the exact IEEE division evaluated.
 __device__ __forceinline__ bool nms_overlap(const float4& a, float area_a, const float4& b, float area_b, float thr) {
   const float w = fmaxf(0.0f, fminf(a.z, b.z) - fmaxf(a.x, b.x));
   const float h = fmaxf(0.0f, fminf(a.w, b.w) - fmaxf(a.y, b.y));
   const float inter = w * h;
   if (thr >= 0.0f && !(inter > 0.0f)) return false;
   const float uni = (area_a + area_b) - inter;
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(uni));
-  const float q = inter * r;
-  if (fabsf(q - thr) > 1e-5f * fmaxf(fabsf(thr), 1e-30f) && fabsf(q) < 1e30f && uni > 1e-30f && uni < 1e30f) return q > thr;
+  const float tu = thr * uni;
+  if (uni > 1e-30f && uni < 1e30f && inter < 1e30f && thr > 1e-6f && thr < 1e6f) {
+    if (inter > tu * 1.00001f) return true;
+    if (inter < tu * 0.99999f) return false;
+  }
   return inter / uni > thr;
 }
 
@@ -129,91 +131,123 @@ __device__ unsigned long long* block_radix_sort_hi32(unsigned long long* src, un
 }
 
 struct GreedyShared {
+  float4 cbox[2][kNmsChunk];           // staged boxes of the current / next chunk (double buffer)
+  float carea[2][kNmsChunk];
+  int cslot[2][kNmsChunk];
   unsigned long long mask[kNmsChunk];  // intra-chunk suppression rows (bit q: row suppresses column q)
-  unsigned long long alive;            // columns of the current chunk not suppressed by the kept list
+  unsigned alive32[2];                 // columns of the current chunk not suppressed by the kept list
+  unsigned nz32[2];                    // rows whose intra-chunk mask is non-zero
   int kcount;
 };
 
+__device__ __forceinline__ void stage_chunk(GreedyShared* gs, int buf, const unsigned long long* sorted, int c0, int n,
+                                            const float4* box, int t) {
+  if (c0 + t < n) {
+    const int slot = (int)(uint32_t)sorted[c0 + t];
+    const float4 bq = box[slot];
+    gs->cbox[buf][t] = bq;
+    gs->carea[buf][t] = (bq.z - bq.x) * (bq.w - bq.y);
+    gs->cslot[buf][t] = slot;
+  }
+}
+
 // Greedy NMS over candidates already sorted by rank: sorted[p] low word = slot into box[] (xyxy, the
-// boxes the IoU is taken on).  Walks the order in chunks of 64: (a) each candidate is tested against
-// the kept list (warp per candidate, lanes over kept boxes, __any_sync), (b) the 64x64 intra-chunk
-// mask is built with __ballot_sync, (c) warp 0 resolves the chunk serially on register-held rows.
+// boxes the IoU is taken on).  Walks the order in chunks of 64 staged in shared memory:
+//   (a) every candidate of the chunk against the kept list -- thread (r, s) tests candidate r against
+//       kept boxes s, s+8, ... (independent iterations, the kept box is a warp-wide broadcast);
+//   (b) the 64x64 intra-chunk mask, one __ballot_sync per 32 columns (warp per row);
+//   (c) warp 0 resolves the chunk: only alive rows with a non-zero mask need a serial step; the other
+//       warps meanwhile stage the next chunk.
 // Identical keep set to the sequential algorithm: j is dropped iff an earlier KEPT i has IoU > thr.
 // kbox/karea/kslot: kept list (max_keep entries, shared memory).  Returns the kept count (<= max_keep).
 __device__ int block_greedy_nms(const unsigned long long* sorted, int n, const float4* box, float thr, int max_keep,
                                 float4* kbox, float* karea, int* kslot, GreedyShared* gs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) gs->kcount = 0;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    gs->kcount = 0;
+    const int cn0 = min(kNmsChunk, n);
+    gs->alive32[0] = cn0 >= 32 ? 0xffffffffu : ((1u << cn0) - 1u);
+    gs->alive32[1] = cn0 >= 64 ? 0xffffffffu : (cn0 > 32 ? ((1u << (cn0 - 32)) - 1u) : 0u);
+    gs->nz32[0] = gs->nz32[1] = 0u;
+  }
+  if (tid < kNmsChunk) stage_chunk(gs, 0, sorted, 0, n, box, tid);
   __syncthreads();
-  for (int c0 = 0; c0 < n; c0 += kNmsChunk) {
+  int buf = 0;
+  for (int c0 = 0; c0 < n; c0 += kNmsChunk, buf ^= 1) {
     const int kc = gs->kcount;
     if (kc >= max_keep) break;
     const int cn = min(kNmsChunk, n - c0);
-    if (threadIdx.x == 0) gs->alive = 0ull;
-    __syncthreads();
     // (a) against the kept list
-    for (int r = warp; r < cn; r += kNmsWarps) {
-      int slot = (int)(uint32_t)sorted[c0 + r];
-      float4 bj = box[slot];
-      float aj = (bj.z - bj.x) * (bj.w - bj.y);
-      bool dead = false;
-      for (int i0 = 0; i0 < kc && !dead; i0 += 32) {
-        int i = i0 + lane;
-        bool hit = (i < kc) && nms_overlap(kbox[i], karea[i], bj, aj, thr);
-        dead = __any_sync(0xffffffffu, hit);
+    {
+      const int r = tid & (kNmsChunk - 1), s = tid / kNmsChunk;
+      constexpr int S = kNmsThreads / kNmsChunk;
+      if (r < cn && s < kc) {
+        const float4 bj = gs->cbox[buf][r];
+        const float aj = gs->carea[buf][r];
+        bool hit = false;
+        for (int i = s; i < kc; i += S) {
+          if (nms_overlap(kbox[i], karea[i], bj, aj, thr)) {
+            hit = true;
+            break;
+          }
+        }
+        if (hit) atomicAnd(&gs->alive32[r >> 5], ~(1u << (r & 31)));
       }
-      if (!dead && lane == 0) atomicOr(&gs->alive, 1ull << r);
     }
     // (b) intra-chunk mask: row r suppresses column q > r
     for (int r = warp; r < cn; r += kNmsWarps) {
-      int slot = (int)(uint32_t)sorted[c0 + r];
-      float4 br = box[slot];
-      float ar = (br.z - br.x) * (br.w - br.y);
+      const float4 br = gs->cbox[buf][r];
+      const float ar = gs->carea[buf][r];
       unsigned long long row = 0ull;
 #pragma unroll
       for (int h = 0; h < kNmsChunk / 32; ++h) {
-        int q = h * 32 + lane;
+        const int q = h * 32 + lane;
         bool hit = false;
-        if (q > r && q < cn) {
-          float4 bq = box[(int)(uint32_t)sorted[c0 + q]];
-          float aq = (bq.z - bq.x) * (bq.w - bq.y);
-          hit = nms_overlap(br, ar, bq, aq, thr);
-        }
-        unsigned w = __ballot_sync(0xffffffffu, hit);
+        if (q > r && q < cn) hit = nms_overlap(br, ar, gs->cbox[buf][q], gs->carea[buf][q], thr);
+        const unsigned w = __ballot_sync(0xffffffffu, hit);
         row |= (unsigned long long)w << (32 * h);
       }
-      if (lane == 0) gs->mask[r] = row;
+      if (lane == 0) {
+        gs->mask[r] = row;
+        if (row) atomicOr(&gs->nz32[r >> 5], 1u << (r & 31));
+      }
     }
     __syncthreads();
-    // (c) serial resolve on warp 0
+    // (c) resolve on warp 0; warps 1-2 stage the next chunk
     if (warp == 0) {
-      unsigned long long m0 = lane < cn ? gs->mask[lane] : 0ull;
-      unsigned long long m1 = lane + 32 < cn ? gs->mask[lane + 32] : 0ull;
-      unsigned long long remaining = gs->alive, kept = 0ull;
-      while (remaining) {
-        int j = __ffsll((long long)remaining) - 1;
-        kept |= 1ull << j;
-        unsigned long long mine = j < 32 ? m0 : m1;
-        unsigned long long row = __shfl_sync(0xffffffffu, mine, j & 31);
-        remaining &= ~row;
-        remaining &= ~(1ull << j);
+      unsigned long long remaining = ((unsigned long long)gs->alive32[1] << 32) | gs->alive32[0];
+      const unsigned long long nz = ((unsigned long long)gs->nz32[1] << 32) | gs->nz32[0];
+      unsigned long long todo = remaining & nz;
+      while (todo) {  // warp-uniform
+        const int j = __ffsll((long long)todo) - 1;
+        remaining &= ~gs->mask[j];
+        todo = remaining & nz & ~((2ull << j) - 1ull);
       }
-      int room = max_keep - kc;
+      const unsigned long long kept = remaining;
+      const int room = max_keep - kc;
 #pragma unroll
       for (int h = 0; h < kNmsChunk / 32; ++h) {
-        int q = h * 32 + lane;
+        const int q = h * 32 + lane;
         if ((kept >> q) & 1ull) {
-          int rank = __popcll(kept & ((1ull << q) - 1ull));
+          const int rank = __popcll(kept & ((1ull << q) - 1ull));
           if (rank < room) {
-            int slot = (int)(uint32_t)sorted[c0 + q];
-            float4 bq = box[slot];
-            kbox[kc + rank] = bq;
-            karea[kc + rank] = (bq.z - bq.x) * (bq.w - bq.y);
-            kslot[kc + rank] = slot;
+            kbox[kc + rank] = gs->cbox[buf][q];
+            karea[kc + rank] = gs->carea[buf][q];
+            kslot[kc + rank] = gs->cslot[buf][q];
           }
         }
       }
-      if (lane == 0) gs->kcount = kc + min(room, __popcll(kept));
+      __syncwarp();
+      if (lane == 0) {
+        gs->kcount = kc + min(room, __popcll(kept));
+        const int cn1 = min(kNmsChunk, max(0, n - c0 - kNmsChunk));
+        gs->alive32[0] = cn1 >= 32 ? 0xffffffffu : ((1u << cn1) - 1u);
+        gs->alive32[1] = cn1 >= 64 ? 0xffffffffu : (cn1 > 32 ? ((1u << (cn1 - 32)) - 1u) : 0u);
+        gs->nz32[0] = gs->nz32[1] = 0u;
+      }
+    } else if (warp <= kNmsChunk / 32) {
+      stage_chunk(gs, buf ^ 1, sorted, c0 + kNmsChunk, n, box, tid - 32);
     }
     __syncthreads();
   }

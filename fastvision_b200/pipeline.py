@@ -2,9 +2,10 @@
 reference's ``Fit._val`` (utils/fit.py:86-95) without its per-image Python loop and host syncs.
 
 Kernel sequence per step (5 launches, optionally replayed as one CUDA graph):
-    decode (+ NMS candidate bitmap + zero-target objectness BCE partials)      fvb_yolo_decode_f32
-    NMS for every image                                                          fvb_yolo_nms_f32
-    loss_prep, loss_match, loss_finalize                                         fvb_yolov3_loss_f32
+    decode (+ NMS candidate bitmap/records + zero-target objectness BCE partials)   fvb_yolo_decode_f32
+    then two independent branches:
+      NMS for every image                                                          fvb_yolo_nms_f32
+      loss_prep, loss_match, loss_finalize (second stream)                         fvb_yolov3_loss_f32
 Under ``torch.distributed`` the batch is sharded per image: every rank runs the same step on its slice
 and the only collective is an all-reduce of the L*4 fp64 loss partials; decode and NMS need none.
 """
@@ -39,6 +40,9 @@ class ValStep:
         self.ctx = None
         self.graph = None
         self.out = None
+        self._side = None
+        self._ev_decoded = None
+        self._ev_loss = None
 
     def _prepare(self, heads):
         ctx = DecodeContext(heads, self.anchors_per_level, self.strides)
@@ -60,26 +64,43 @@ class ValStep:
         ctx.records()
         ctx.bce0()
         self.graph = None
+        # NMS (latency-bound, one CTA per image) and the loss kernels only depend on the decode: they run as
+        # two branches (second stream; two parallel branches of the graph when captured)
+        self._side = torch.cuda.Stream(device=dev)
+        self._ev_decoded = torch.cuda.Event()
+        self._ev_loss = torch.cuda.Event()
 
     def _distributed(self):
         return self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                        and torch.distributed.get_world_size() > 1)
 
-    def _run(self, heads, labels):
+    def _decode(self, heads):
         ctx, o = self.ctx, self.out
         yolov3_decode(heads, self.anchors_per_level, self.strides, precise=self.precise, ctx=ctx, out=o["results"],
                       conf_thres=self.conf_thres, want_bce0=True)
+
+    def _tail(self, heads, labels):
+        """Everything after the decode: the NMS branch and the loss branch (second stream), joined at the end."""
+        ctx, o = self.ctx, self.out
+        main = torch.cuda.current_stream()
+        self._ev_decoded.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_decoded)
+            self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
+            if self._distributed():
+                torch.distributed.all_reduce(o["partials"], group=self.pg)     # 96 bytes; the only collective
+                bg = self.batch_global or ctx.batch * torch.distributed.get_world_size(self.pg)
+                self.loss_fn.combine(o["partials"], bg, ctx=ctx, out=o["loss"])
+            self._ev_loss.record(self._side)
         non_max_suppression_batched(o["results"], self.conf_thres, self.iou_thres, self.max_det, self.nms_flavour,
                                     cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=True,
                                     out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]))
-        if self._distributed():
-            self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
-            torch.distributed.all_reduce(o["partials"], group=self.pg)     # 96 bytes; the only collective
-            bg = self.batch_global or ctx.batch * torch.distributed.get_world_size(self.pg)
-            self.loss_fn.combine(o["partials"], bg, ctx=ctx, out=o["loss"])
-        else:
-            self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
-        return o
+        main.wait_event(self._ev_loss)
+
+    def _run(self, heads, labels):
+        self._decode(heads)
+        self._tail(heads, labels)
+        return self.out
 
     def __call__(self, head_out: List[torch.Tensor], labels: torch.Tensor):
         """head_out: raw [B,A,H,W,K] per level (this rank's images); labels [T,6] with LOCAL batch indices.
@@ -92,22 +113,31 @@ class ValStep:
         self._prepare(heads)
         return self._run(heads, labels)
 
-    def capture(self, head_out, labels):
-        """Capture the step for these (static) input tensors into a CUDA graph; returns a replay callable."""
+    def capture(self, head_out, labels, split_decode=False):
+        """Capture the step for these (static) input tensors into a CUDA graph; returns a replay callable.
+
+        With ``split_decode`` only the part after the decode is captured and ``(decode_fn, tail_replay)`` is
+        returned, so a caller can bracket the (eagerly launched) decode kernel with timing events.
+        """
         heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
         labels = _lib.require_cuda(labels, "labels").view(-1, 6)
         self._prepare(heads)
-        side = torch.cuda.Stream(device=self.ctx.device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        warm = torch.cuda.Stream(device=self.ctx.device)
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
             for _ in range(2):          # warm-up: sizes every cached workspace outside the capture
                 self._run(heads, labels)
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream().wait_stream(warm)
         torch.cuda.synchronize(self.ctx.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._run(heads, labels)
+            if split_decode:
+                self._tail(heads, labels)
+            else:
+                self._run(heads, labels)
         self.graph = g
+        if split_decode:
+            return (lambda: self._decode(heads)), g.replay
         return g.replay
 
     def detections(self, out=None):
