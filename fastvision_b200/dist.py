@@ -1,0 +1,71 @@
+"""Data-parallel plumbing for the hot path: one process per GPU, images sharded contiguously.
+
+Decode and NMS are per image and need no collective.  The loss normalisers are GLOBAL-batch
+(loss/yolov3_loss.py:52,58,64): ranks all-reduce the L*4 fp64 partial sums {S_cls, S_box, S_conf, M} and
+every rank forms the scalar with the global batch size.  mAP needs the ``correct`` rows and the target
+classes of all ranks on the rank that calls ``fetch`` (all-gather of padded rows).
+Works with any torch.distributed backend (nccl on GPUs; gloo in the CPU tests of the host logic).
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(batch_global: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [start, stop) of the global batch owned by ``rank`` (remainder spread over low ranks)."""
+    base, rem = divmod(batch_global, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_labels(labels: torch.Tensor, start: int, stop: int) -> torch.Tensor:
+    """Rows of ``labels`` [T,6] whose image index lies in [start, stop), re-based to local image indices."""
+    keep = (labels[:, 0] >= start) & (labels[:, 0] < stop)
+    out = labels[keep].clone()
+    out[:, 0] -= start
+    return out
+
+
+def allreduce_partials(partials: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the [L,4] fp64 loss partials over ranks, in place (96 bytes; latency-bound)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+    return partials
+
+
+def combine_partials_host(partials, cells_per_image_level: List[int], num_classes: int, batch_global: int,
+                          ratio_box: float = 0.05, ratio_conf: float = 1.0, ratio_cls: float = 0.5) -> float:
+    """Host mirror of ``fvb_yolov3_loss_combine_f32`` (the formula of loss/yolov3_loss.py:49-72 on global sums).
+
+    partials[l] = (S_cls, S_box, S_conf, M); cells_per_image_level[l] = A*H_l*W_l.
+    """
+    total = 0.0
+    for l, cells in enumerate(cells_per_image_level):
+        s_cls, s_box, s_conf, m = (float(x) for x in partials[l])
+        if m > 0:
+            total += ratio_cls * s_cls / (m * num_classes) + ratio_box * s_box / m
+        total += ratio_conf * s_conf / (float(batch_global) * cells)
+    return total * batch_global
+
+
+def all_gather_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate a per-rank [n_r, C] tensor over ranks (rank order), n_r may differ: counts, then padded rows."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rows
+    world = dist.get_world_size(group)
+    n = torch.tensor([rows.size(0)], dtype=torch.int64, device=rows.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.zeros((cap,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    padded[:rows.size(0)] = rows
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def gather_map_state(correct_rows: torch.Tensor, target_classes: torch.Tensor, group=None):
+    """Bring every rank's mAP evidence together: ``correct`` rows [sum M, 2+n_thr] and target classes [sum N]."""
+    return all_gather_rows(correct_rows, group), all_gather_rows(target_classes.view(-1, 1), group).view(-1)

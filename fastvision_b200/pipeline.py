@@ -148,9 +148,4 @@ class ValStep:
         return [dets[i, :c] for i, c in enumerate(cnt)]
 
 
-def shard_labels(labels: torch.Tensor, start: int, stop: int) -> torch.Tensor:
-    """Rows of ``labels`` whose image index lies in [start, stop), re-based to local indices."""
-    keep = (labels[:, 0] >= start) & (labels[:, 0] < stop)
-    out = labels[keep].clone()
-    out[:, 0] -= start
-    return out
+from .dist import shard_labels  # noqa: E402,F401  (re-exported: tests and callers import it from here)
