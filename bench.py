@@ -303,7 +303,9 @@ def run_cuda(args, cfg):
                        "conf_thres": 0.25, "iou_thres": 0.45, "max_det": 300, "loss_ratios": [0.05, 1.0, 0.5],
                        "labels": int(labels.size(0)), "parallelism": "per-image sharding, dp%d" % world,
                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2; no flush needed" % (alg_bytes / 2e6),
-                       "step_launch": "decode launched eagerly between CUDA events, NMS + loss branches replayed as a CUDA graph"},
+                       "step_launch": ("decode launched eagerly between CUDA events; NMS branch and loss branch (+ NCCL all-reduce of the "
+                                       "12 fp64 partials) launched eagerly on two streams" if distributed else
+                                       "decode launched eagerly between CUDA events, NMS + loss branches replayed as a CUDA graph")},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": ke, "note": "pinned host heads+labels copied H2D, ValStep public call, loss + padded detections copied D2H, every step"},

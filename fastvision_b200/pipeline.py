@@ -79,27 +79,37 @@ class ValStep:
         yolov3_decode(heads, self.anchors_per_level, self.strides, precise=self.precise, ctx=ctx, out=o["results"],
                       conf_thres=self.conf_thres, want_bce0=True)
 
-    def _tail(self, heads, labels):
-        """Everything after the decode: the NMS branch and the loss branch (second stream), joined at the end."""
+    def _tail(self, heads, labels, reduce_inside=False):
+        """Everything after the decode: the NMS branch and the loss branch (second stream), joined at the end.
+        ``reduce_inside`` puts the data-parallel all-reduce + combine into the loss branch so that it hides under
+        the (longer) NMS branch; only possible when the tail is launched eagerly, not captured."""
         ctx, o = self.ctx, self.out
         main = torch.cuda.current_stream()
         self._ev_decoded.record(main)
         with torch.cuda.stream(self._side):
             self._side.wait_event(self._ev_decoded)
             self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
-            if self._distributed():
-                torch.distributed.all_reduce(o["partials"], group=self.pg)     # 96 bytes; the only collective
-                bg = self.batch_global or ctx.batch * torch.distributed.get_world_size(self.pg)
-                self.loss_fn.combine(o["partials"], bg, ctx=ctx, out=o["loss"])
+            if reduce_inside:
+                self._reduce()
             self._ev_loss.record(self._side)
         non_max_suppression_batched(o["results"], self.conf_thres, self.iou_thres, self.max_det, self.nms_flavour,
                                     cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=True,
                                     out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]))
         main.wait_event(self._ev_loss)
 
+    def _reduce(self):
+        """Data-parallel only: all-reduce the per-level partial sums (96 bytes, the ONLY collective of the step) and
+        form the scalar with the global-batch normalisers.  Kept outside the captured graph (plain NCCL launch)."""
+        if not self._distributed():
+            return
+        o, ctx = self.out, self.ctx
+        torch.distributed.all_reduce(o["partials"], group=self.pg)
+        bg = self.batch_global or ctx.batch * torch.distributed.get_world_size(self.pg)
+        self.loss_fn.combine(o["partials"], bg, ctx=ctx, out=o["loss"])
+
     def _run(self, heads, labels):
         self._decode(heads)
-        self._tail(heads, labels)
+        self._tail(heads, labels, reduce_inside=True)
         return self.out
 
     def __call__(self, head_out: List[torch.Tensor], labels: torch.Tensor):
@@ -122,6 +132,11 @@ class ValStep:
         heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
         labels = _lib.require_cuda(labels, "labels").view(-1, 6)
         self._prepare(heads)
+        if self._distributed():
+            # data-parallel: keep the NCCL all-reduce out of any graph and inside the loss branch (overlaps the NMS)
+            if split_decode:
+                return (lambda: self._decode(heads)), (lambda: self._tail(heads, labels, reduce_inside=True))
+            return lambda: self._run(heads, labels)
         warm = torch.cuda.Stream(device=self.ctx.device)
         warm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(warm):
@@ -131,11 +146,11 @@ class ValStep:
         torch.cuda.synchronize(self.ctx.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            if split_decode:
-                self._tail(heads, labels)
-            else:
-                self._run(heads, labels)
+            if not split_decode:
+                self._decode(heads)
+            self._tail(heads, labels)
         self.graph = g
+
         if split_decode:
             return (lambda: self._decode(heads)), g.replay
         return g.replay
