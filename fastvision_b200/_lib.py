@@ -36,7 +36,7 @@ _SIGS = {
     "fvb_launch_count": (C.c_uint64, []),
     "fvb_yolo_rows_per_image": (C.c_int, [C.POINTER(Geom)]),
     "fvb_yolo_bitmap_words": (C.c_int, [C.POINTER(Geom)]),
-    "fvb_yolo_decode_tiles": (C.c_int, [C.POINTER(Geom)]),
+    "fvb_yolo_decode_partials": (C.c_int, [C.POINTER(Geom)]),
     "fvb_yolo_decode_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), C.c_int, C.c_int, _P, C.c_float, _P, _P, _P, _P]),
     "fvb_box_convert_f32": (C.c_int, [_P, C.c_int64, C.c_int, C.c_float, C.c_float, _P, _P]),
     "fvb_iou_elementwise_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
@@ -51,7 +51,7 @@ _SIGS = {
                                    _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "fvb_rpn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fvb_rpn_proposals_f32": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                        C.c_double, _P, _P, _P, _P]),
+                                        C.c_double, _P, _P, _P, _P, _P]),
     "fvb_yolov3_loss_workspace_bytes": (C.c_size_t, [C.POINTER(Geom), C.c_int64]),
     "fvb_yolov3_loss_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_float, C.c_float, C.c_float,
                                       _P, _P, _P, _P, _P]),

@@ -39,15 +39,38 @@ struct Geom {
 
 int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out);
 
-static const int kDecodeThreads = 256;
+static const int kDecodeThreads = 512;
+// Shared memory the persistent decode kernel may take per SM: leaves room for one NMS CTA (~112 KB) beside it.
+static const size_t kDecodeSmemBudget = 112 * 1024;
 
-// The decode kernel's work unit: one warp x 32 consecutive rows of one (image, level) segment, 8 warps
-// per CTA, CTAs never straddle levels.  It also defines the layout of the fused objectness-BCE
-// partials: [B][blocks per image], blocks of an image ordered level by level.
-inline int decode_blocks_level(const Geom& g, int l) { return (g.A * g.HW[l] + 255) / 256; }
+// Launch shape of the decode kernel (decode.cu); also fixes the layout of the fused objectness-BCE partials:
+// [L][grid * warps_per_cta] doubles, one per warp of the grid and level.
+struct DecodeShape {
+  int tile_rows, tile_floats;
+  int tiles_level_end[FVB_MAX_LEVELS];
+  int tiles_per_image;
+  long long total_tiles;
+  int warps_per_cta, grid, stages;
+  size_t smem_bytes;
+};
+int decode_launch_shape(const Geom& g, DecodeShape* s);
 
 // ---- device math, written to mirror torch's fp32 op order ------------------------------------------
 __device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// MUFU forms used by the streaming kernels: <= 2.5e-6 relative to torch's sigmoid for |x| <= 30
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(x * -kLog2e)); }
 
 // -t*log(p+1e-8) - (1-t)*log(1-p+1e-8), loss/classification_loss.py:55, evaluated exactly in that form.
 __device__ __forceinline__ float bce_term(float p, float t) {
@@ -55,6 +78,9 @@ __device__ __forceinline__ float bce_term(float p, float t) {
   float b = (1.0f - t) * logf((1.0f - p) + 1e-8f);
   return a - b;
 }
+
+// The same expression with t = 0: the first product is (-0)*finite = +-0, so the result is exactly 0 - 1*log(...).
+__device__ __forceinline__ float bce_term_zero(float p) { return 0.0f - logf((1.0f - p) + 1e-8f); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

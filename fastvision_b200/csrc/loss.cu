@@ -175,15 +175,16 @@ __global__ void __launch_bounds__(256) conf_stream_kernel(const StreamParams p) 
   const int b = id / p.chunks[l], ch = id - b * p.chunks[l];
   const int rows = p.g.A * p.g.HW[l];
   const float* base = p.g.head[l] + (size_t)b * rows * p.g.K + 4;
-  float acc = 0.0f;
+  double acc = 0.0;
   const int r0 = ch * kStreamRows;
 #pragma unroll
   for (int i = 0; i < kStreamRows / 256; ++i) {
     int r = r0 + i * 256 + threadIdx.x;
-    if (r < rows) acc += bce_term(sigmoid_precise(__ldg(base + (size_t)r * p.g.K)), 0.0f);
+    // same arithmetic as the fused partials of the decode kernel: objectness as decode stores it, target 0
+    if (r < rows) acc += (double)bce_term_zero(sigmoid_fast(__ldg(base + (size_t)r * p.g.K)));
   }
   __shared__ double scratch[32];
-  double s = block_sum((double)acc, scratch);
+  double s = block_sum(acc, scratch);
   if (threadIdx.x == 0) p.partials[blockIdx.x] = s;
 }
 
@@ -409,11 +410,13 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
   fp.batch_global = g.B;
   if (d_conf_bce0) {
     fp.conf0 = d_conf_bce0;
-    int t = 0;
+    DecodeShape sh;
+    rc = decode_launch_shape(g, &sh);  // the decode kernel wrote one partial per warp of its grid and level
+    if (rc != FVB_OK) return rc;
+    const int nw = sh.grid * sh.warps_per_cta;
     for (int l = 0; l < g.L; ++l) {
-      fp.level_begin[l] = t;
-      t += decode_blocks_level(g, l) * g.B;
-      fp.level_end[l] = t;
+      fp.level_begin[l] = l * nw;
+      fp.level_end[l] = (l + 1) * nw;
     }
   } else {
     StreamParams sp;

@@ -68,7 +68,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 // Stable LSD radix sort of n 64-bit keys by their HIGH 32 bits, ascending.  Keys must enter in the
 // order that should break ties (low word = slot index, already ascending).  Returns the buffer that
 // holds the sorted keys.  cnt: kNmsWarps*256 u32, warp_tot: kNmsWarps+1 u32 (shared memory).
-__device__ unsigned long long* block_radix_sort_hi32(unsigned long long* src, unsigned long long* dst, int n,
+__device__ inline unsigned long long* block_radix_sort_hi32(unsigned long long* src, unsigned long long* dst, int n,
                                                      uint32_t* cnt, uint32_t* warp_tot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -160,7 +160,7 @@ __device__ __forceinline__ void stage_chunk(GreedyShared* gs, int buf, const uns
 //       warps meanwhile stage the next chunk.
 // Identical keep set to the sequential algorithm: j is dropped iff an earlier KEPT i has IoU > thr.
 // kbox/karea/kslot: kept list (max_keep entries, shared memory).  Returns the kept count (<= max_keep).
-__device__ int block_greedy_nms(const unsigned long long* sorted, int n, const float4* box, float thr, int max_keep,
+__device__ inline int block_greedy_nms(const unsigned long long* sorted, int n, const float4* box, float thr, int max_keep,
                                 float4* kbox, float* karea, int* kslot, GreedyShared* gs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tid = threadIdx.x;

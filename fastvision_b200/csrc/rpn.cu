@@ -1,16 +1,180 @@
-// RPN proposal filter (demos/faster_rcnn/models/rpn.py:168-208) -- implemented in a later milestone.
-#include "common.cuh"
+// Faster R-CNN RPN proposal filter for a whole batch: 2 launches, no host sync.
+//
+// Replaces RPN.filter_proposals (demos/faster_rcnn/models/rpn.py:168-208) and what it calls:
+// make_anchors_xywh :160-166, dxdydwdh2xywh :111-119, xywh2xyxy :131-137, the per-image Python loop of
+// topk -> torchvision.ops.nms -> first post_n -> xyxy2xywh :139-145.
+//   rpn_decode_kernel   one thread per anchor: reads its 16-byte regression and 8-byte class pair once,
+//                       writes the clamped xyxy box and a 64-bit sort key (descending score, anchor index);
+//   rpn_nms_kernel      one CTA per image: block radix sort of all H*W*A keys (the reference's topk is the
+//                       first pre_n of that order), chunked greedy suppression over the first pre_n with the
+//                       kept list (<= post_n boxes) in shared memory, xywh outputs + count.
+// Ties: equal scores rank by lower anchor index (torch.topk leaves tie order unspecified).
+#include "nms.cuh"
+
+#include <math.h>
+
+namespace fvb {
+
+struct RpnParams {
+  const float* cls;  // [B,H,W,A,2]
+  const float* reg;  // [B,H,W,A,4]
+  int B, H, W, A, n;  // n = H*W*A
+  float aw[FVB_MAX_ANCHORS], ah[FVB_MAX_ANCHORS];
+  int pre_n, post_n;  // post_n already clipped to n
+  int out_pitch;      // rows per image of the padded outputs (the caller's post_n)
+  float iou_thr;
+  unsigned long long* keys;  // [B][2][n]
+  float4* box;               // [B][n] clamped xyxy, feature units
+  float* out_xywh;           // [B][post_n][4]
+  int* out_idx;              // [B][post_n] anchor index (h,w,a flat) of every proposal, or NULL
+  int* out_cnt;              // [B]
+};
+
+__global__ void __launch_bounds__(256) rpn_decode_kernel(const RpnParams p) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= p.n) return;
+  const int cell = i / p.A, a = i - cell * p.A;
+  const int y = cell / p.W, x = cell - y * p.W;
+  const size_t g = (size_t)b * p.n + i;
+  const float4 d = reinterpret_cast<const float4*>(p.reg)[g];
+  const float2 c = reinterpret_cast<const float2*>(p.cls)[g];
+  const float aw = p.aw[a], ah = p.ah[a];
+  // rpn.py:114-117 (h uses exp(dw), sic)
+  const float bx = d.x * aw + (float)x;
+  const float by = d.y * ah + (float)y;
+  const float e = expf(d.z);
+  const float bw = e * aw, bh = e * ah;
+  // softmax over the pair, torch op order: subtract the max, exp, normalise (rpn.py:173-175)
+  const float m = fmaxf(c.x, c.y);
+  const float e0 = expf(c.x - m), e1 = expf(c.y - m);
+  const float score = e1 / (e0 + e1);
+  // rpn.py:181-185: xyxy, clamped to the feature map
+  const float hw = bw / 2.0f, hh = bh / 2.0f;
+  const float xmax = (float)(p.W - 1), ymax = (float)(p.H - 1);
+  float4 o;
+  o.x = fminf(fmaxf(bx - hw, 0.0f), xmax);
+  o.y = fminf(fmaxf(by - hh, 0.0f), ymax);
+  o.z = fminf(fmaxf(bx + hw, 0.0f), xmax);
+  o.w = fminf(fmaxf(by + hh, 0.0f), ymax);
+  p.box[g] = o;
+  p.keys[(size_t)b * 2 * p.n + i] = ((unsigned long long)desc_key(score) << 32) | (uint32_t)i;
+}
+
+struct RpnSmemLayout {
+  size_t cnt, warp_tot, kbox, karea, kslot, gs, total;
+};
+
+__host__ __device__ inline RpnSmemLayout rpn_layout(int max_keep) {
+  RpnSmemLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    o = (o + 15) / 16 * 16;
+    size_t r = o;
+    o += bytes;
+    return r;
+  };
+  L.cnt = take((size_t)kNmsWarps * 256 * 4);
+  L.warp_tot = take((size_t)(kNmsWarps + 1) * 4);
+  L.kbox = take((size_t)max_keep * 16);
+  L.karea = take((size_t)max_keep * 4);
+  L.kslot = take((size_t)max_keep * 4);
+  L.gs = take(sizeof(GreedyShared));
+  L.total = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(kNmsThreads) rpn_nms_kernel(const RpnParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const RpnSmemLayout L = rpn_layout(p.post_n);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L.cnt);
+  uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + L.warp_tot);
+  float4* kbox = reinterpret_cast<float4*>(smem + L.kbox);
+  float* karea = reinterpret_cast<float*>(smem + L.karea);
+  int* kslot = reinterpret_cast<int*>(smem + L.kslot);
+  GreedyShared* gs = reinterpret_cast<GreedyShared*>(smem + L.gs);
+  const int b = blockIdx.x;
+  unsigned long long* keys0 = p.keys + (size_t)b * 2 * p.n;
+  const float4* box = p.box + (size_t)b * p.n;
+  unsigned long long* sorted = block_radix_sort_hi32(keys0, keys0 + p.n, p.n, cnt, warp_tot);
+  const int n_use = min(p.pre_n, p.n);  // rpn.py:193-195 topk
+  const int kept = block_greedy_nms(sorted, n_use, box, p.iou_thr, p.post_n, kbox, karea, kslot, gs);
+  for (int i = threadIdx.x; i < kept; i += kNmsThreads) {
+    const float4 q = kbox[i];
+    // rpn.py:139-145 xyxy2xywh
+    const float4 o = make_float4((q.x + q.z) / 2.0f, (q.y + q.w) / 2.0f, q.z - q.x, q.w - q.y);
+    reinterpret_cast<float4*>(p.out_xywh)[(size_t)b * p.out_pitch + i] = o;
+    if (p.out_idx) p.out_idx[(size_t)b * p.out_pitch + i] = kslot[i];
+  }
+  if (threadIdx.x == 0) p.out_cnt[b] = kept;
+}
+
+static size_t rpn_align(size_t x) { return (x + 255) / 256 * 256; }
+
+}  // namespace fvb
+
+using namespace fvb;
 
 extern "C" size_t fvb_rpn_workspace_bytes(int batch, int height, int width, int anchors) {
-  (void)batch; (void)height; (void)width; (void)anchors;
-  return 256;
+  if (batch < 0 || height < 0 || width < 0 || anchors < 0) return 0;
+  const size_t bn = (size_t)batch * height * width * anchors;
+  return rpn_align(bn * 2 * 8) + rpn_align(bn * 16) + 256;
 }
 
 extern "C" int fvb_rpn_proposals_f32(const float* d_cls, const float* d_reg, const float* base_anchors, int batch,
                                      int height, int width, int anchors, int pre_n, int post_n, double iou_thr,
-                                     float* d_out_xywh, int32_t* d_out_cnt, void* d_ws, void* stream) {
-  (void)d_cls; (void)d_reg; (void)base_anchors; (void)batch; (void)height; (void)width; (void)anchors;
-  (void)pre_n; (void)post_n; (void)iou_thr; (void)d_out_xywh; (void)d_out_cnt; (void)d_ws; (void)stream;
-  fvb::set_error("rpn_proposals: not implemented yet");
-  return FVB_E_LIMIT;
+                                     float* d_out_xywh, int32_t* d_out_idx, int32_t* d_out_cnt, void* d_ws,
+                                     void* stream) {
+  FVB_REQUIRE(batch >= 0 && batch <= 65535 && height >= 1 && width >= 1, "rpn_proposals: bad shape B=%d H=%d W=%d", batch, height, width);
+  FVB_REQUIRE(anchors >= 1 && anchors <= FVB_MAX_ANCHORS, "rpn_proposals: anchors=%d out of range [1,%d]", anchors, FVB_MAX_ANCHORS);
+  FVB_REQUIRE(pre_n >= 1 && post_n >= 1, "rpn_proposals: pre_n=%d post_n=%d", pre_n, post_n);
+  FVB_REQUIRE(d_cls && d_reg && base_anchors && d_out_xywh && d_out_cnt && d_ws, "rpn_proposals: NULL pointer");
+  FVB_REQUIRE(((uintptr_t)d_reg & 15) == 0 && ((uintptr_t)d_cls & 7) == 0 && ((uintptr_t)d_out_xywh & 15) == 0 && ((uintptr_t)d_ws & 255) == 0,
+              "rpn_proposals: reg/out_xywh must be 16-byte, cls 8-byte and the workspace 256-byte aligned");
+  const long long n = (long long)height * width * anchors;
+  if (n >= (1ll << 31)) {
+    set_error("rpn_proposals: %lld anchors per image", n);
+    return FVB_E_LIMIT;
+  }
+  if (batch == 0) return FVB_OK;
+  RpnParams p;
+  p.cls = d_cls;
+  p.reg = d_reg;
+  p.B = batch;
+  p.H = height;
+  p.W = width;
+  p.A = anchors;
+  p.n = (int)n;
+  for (int a = 0; a < anchors; ++a) {
+    p.aw[a] = base_anchors[2 * a];
+    p.ah[a] = base_anchors[2 * a + 1];
+  }
+  p.pre_n = pre_n;
+  p.post_n = (int)(post_n < n ? post_n : n);  // rpn.py:201: never more than the survivors
+  const float t = (float)iou_thr;
+  p.iou_thr = ((double)t > iou_thr) ? nextafterf(t, -INFINITY) : t;  // fp32 ratio vs double threshold (nms.cu)
+  const size_t bn = (size_t)batch * (size_t)n;
+  p.keys = (unsigned long long*)d_ws;
+  p.box = (float4*)((unsigned char*)d_ws + rpn_align(bn * 2 * 8));
+  p.out_xywh = d_out_xywh;
+  p.out_idx = d_out_idx;
+  p.out_cnt = d_out_cnt;
+  p.out_pitch = post_n;
+  RpnSmemLayout L = rpn_layout(p.post_n);
+  if (L.total > 227 * 1024) {
+    set_error("rpn_proposals: post_n=%d needs %zu bytes of shared memory for the kept list", post_n, L.total);
+    return FVB_E_LIMIT;
+  }
+  cudaError_t e = cudaFuncSetAttribute((const void*)rpn_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  if (e != cudaSuccess) {
+    set_error("rpn_proposals: cudaFuncSetAttribute(%zu): %s", L.total, cudaGetErrorString(e));
+    return FVB_E_CUDA;
+  }
+  cudaStream_t cs = (cudaStream_t)stream;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)batch);
+  rpn_decode_kernel<<<grid, 256, 0, cs>>>(p);
+  count_launch();
+  rpn_nms_kernel<<<batch, kNmsThreads, L.total, cs>>>(p);
+  count_launch();
+  return check_launch("rpn_nms_kernel");
 }

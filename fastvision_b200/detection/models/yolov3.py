@@ -31,7 +31,7 @@ class DecodeContext:
         if self.rows < 0:
             _lib.check(-1, "geometry")
         self.words = lib.fvb_yolo_bitmap_words(self.geom)
-        self.tiles = lib.fvb_yolo_decode_tiles(self.geom)
+        self._n_partials = None
         self.device = h0.device
         self.key = (self.batch, self.num_anchors, self.k, tuple(self.heights), tuple(self.widths), self.device)
         self._bitmap = None
@@ -51,7 +51,11 @@ class DecodeContext:
 
     def bce0(self):
         if self._bce0 is None:
-            self._bce0 = torch.empty(self.batch * self.tiles, dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):      # the partial layout follows the decode grid of THIS device
+                n = _lib.load().fvb_yolo_decode_partials(self.geom)
+            if n < 0:
+                _lib.check(-2, "decode_partials")
+            self._bce0 = torch.empty(n, dtype=torch.float64, device=self.device)
         return self._bce0
 
 

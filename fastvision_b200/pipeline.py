@@ -163,4 +163,104 @@ class ValStep:
         return [dets[i, :c] for i, c in enumerate(cnt)]
 
 
+class ValPipeline:
+    """Software-pipelined validation loop: the NMS + loss tail of batch i overlaps the decode of batch i+1.
+
+    ``Fit._val`` (utils/fit.py:86-105) walks the validation set batch by batch; nothing in batch i+1's decode
+    depends on batch i's detections, so the latency-bound NMS (one CTA per image) and the tiny loss kernels run
+    on two side streams while the main stream already streams the next batch through the (HBM-bound, persistent)
+    decode kernel, which leaves shared memory for one NMS CTA per SM.  Two buffer sets (results, candidate bitmap /
+    records, objectness partials, padded detections, loss) alternate; ``submit`` waits on the events of the set
+    it is about to overwrite, so outputs of batch i stay valid until batch i+2 is submitted.
+    Under ``torch.distributed`` the 96-byte all-reduce of the loss partials sits in the loss branch.
+    """
+
+    def __init__(self, anchors_per_level, strides, depth=2, **kw):
+        self.steps = [ValStep(anchors_per_level, strides, **kw) for _ in range(depth)]
+        self.depth = depth
+        self.count = 0
+        self._dec_stream = None
+        self._nms_stream = None
+        self._loss_stream = None
+        self._done = [None] * depth
+
+    def _streams(self, dev):
+        if self._nms_stream is None:
+            lo, hi = torch.cuda.Stream.priority_range()      # (least, greatest) = (0, -k)
+            # the decode grid (one persistent CTA per SM) must be placed first; NMS CTAs then take the shared memory
+            # it leaves (one per SM).  With the priorities the other way round two NMS CTAs per SM would lock the
+            # decode out until they finish -- no overlap at all.
+            self._dec_stream = torch.cuda.Stream(device=dev, priority=hi)
+            self._nms_stream = torch.cuda.Stream(device=dev, priority=lo)
+            self._loss_stream = torch.cuda.Stream(device=dev, priority=lo)
+            self._done = [(torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()) for _ in range(self.depth)]
+            self._ev_in = [torch.cuda.Event() for _ in range(self.depth)]
+        return self._dec_stream, self._nms_stream, self._loss_stream
+
+    def submit(self, head_out: List[torch.Tensor], labels: torch.Tensor, decode_events=None, trace=None):
+        """Enqueue one batch; returns the dict of output buffers of this slot (valid after ``wait(slot)``/``flush``).
+
+        ``decode_events``: optional (start, stop) CUDA events recorded around the decode kernel on its stream.
+        ``trace``: optional dict name -> (start, stop) timing events for "nms" / "loss" (tools/pipeline_trace.py).
+        """
+        slot = self.count % self.depth
+        st = self.steps[slot]
+        heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
+        labels = _lib.require_cuda(labels, "labels").view(-1, 6)
+        st._prepare(heads)
+        dec_s, nms_s, loss_s = self._streams(st.ctx.device)
+        ev_dec, ev_nms, ev_loss = self._done[slot]
+        ev_in = self._ev_in[slot]
+        ev_in.record(torch.cuda.current_stream())    # inputs are ready once the caller's stream gets here
+        o, ctx = st.out, st.ctx
+        with torch.cuda.stream(dec_s):
+            dec_s.wait_event(ev_in)
+            if self.count >= self.depth:             # the slot's previous tail must have consumed its buffers
+                dec_s.wait_event(ev_nms)
+                dec_s.wait_event(ev_loss)
+            if decode_events is not None:
+                decode_events[0].record(dec_s)
+            st._decode(heads)
+            if decode_events is not None:
+                decode_events[1].record(dec_s)
+            ev_dec.record(dec_s)
+        with torch.cuda.stream(loss_s):
+            loss_s.wait_event(ev_dec)
+            if trace is not None:
+                trace["loss"][0].record(loss_s)
+            st.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
+            st._reduce()
+            if trace is not None:
+                trace["loss"][1].record(loss_s)
+            ev_loss.record(loss_s)
+        with torch.cuda.stream(nms_s):
+            nms_s.wait_event(ev_dec)
+            if trace is not None:
+                trace["nms"][0].record(nms_s)
+            non_max_suppression_batched(o["results"], st.conf_thres, st.iou_thres, st.max_det, st.nms_flavour,
+                                        cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=True,
+                                        out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]))
+            if trace is not None:
+                trace["nms"][1].record(nms_s)
+            ev_nms.record(nms_s)
+        self.count += 1
+        return o
+
+    def wait(self, slot=None):
+        """Make the current stream wait for the tail of ``slot`` (default: the most recently submitted batch)."""
+        if self.count == 0:
+            return
+        slot = (self.count - 1) % self.depth if slot is None else slot
+        ev_dec, ev_nms, ev_loss = self._done[slot]
+        main = torch.cuda.current_stream()
+        main.wait_event(ev_dec)
+        main.wait_event(ev_nms)
+        main.wait_event(ev_loss)
+
+    def flush(self):
+        """Join every outstanding tail into the current stream."""
+        for slot in range(min(self.count, self.depth)):
+            self.wait(slot)
+
+
 from .dist import shard_labels  # noqa: E402,F401  (re-exported: tests and callers import it from here)

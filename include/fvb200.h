@@ -91,14 +91,15 @@ typedef struct {
  *                  {results[b,r,0..3], conf, max_c(cls_c*conf), argmax_c as int bits, unused} -- what
  *                  NMS.py:13-16 computes per candidate, produced while the row is in registers so the
  *                  NMS kernel never re-reads the 4*K-byte rows; non-candidate records are not written;
- *   d_conf_bce0    [fvb_yolo_decode_tiles(geom), B] f64: per-CTA sums (CTAs of an image ordered by level) of
- *                  -log(1 - sigmoid(t4) + 1e-8), the zero-target part of the objectness BCE of
- *                  Yolov3Loss (loss/yolov3_loss.py:63-64), consumed by fvb_yolov3_loss_f32.
+ *   d_conf_bce0    [fvb_yolo_decode_partials(geom)] f64: partial sums (one per warp of the decode grid and
+ *                  level, fixed tile -> warp map, so reproducible) of -log(1 - sigmoid(t4) + 1e-8), the
+ *                  zero-target part of the objectness BCE of Yolov3Loss (loss/yolov3_loss.py:63-64),
+ *                  consumed by fvb_yolov3_loss_f32 on the same device.
  * precise != 0 uses expf + IEEE division instead of ex2.approx/rcp.approx (both meet rtol 1e-5).
  */
 int fvb_yolo_rows_per_image(const fvb_yolo_geom* geom);
 int fvb_yolo_bitmap_words(const fvb_yolo_geom* geom);
-int fvb_yolo_decode_tiles(const fvb_yolo_geom* geom); /* decode CTAs per image = objectness partials per image */
+int fvb_yolo_decode_partials(const fvb_yolo_geom* geom); /* doubles in d_conf_bce0 (needs a CUDA device) */
 int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
                         float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
                         double* d_conf_bce0, void* stream);
@@ -161,16 +162,19 @@ int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_image, int 
 
 /* fvb_rpn_proposals_f32: RPN.filter_proposals, demos/faster_rcnn/models/rpn.py:168-208 (+ :111-119,
  * :160-166).  d_cls [B,H,W,A,2], d_reg [B,H,W,A,4], base_anchors (host) [A,2] (w,h) feature units.
- * Outputs d_out_xywh [B,post_n,4], d_out_cnt [B]. */
+ * The reference's per-image topk(pre_n) -> nms(iou_thr) -> first post_n runs for all images in one launch.
+ * Outputs (padded, entries past d_out_cnt[b] undefined): d_out_xywh [B,post_n,4] feature units, d_out_idx
+ * [B,post_n] int32 = flat (h,w,a) anchor index of each proposal (may be NULL), d_out_cnt [B].
+ * Equal scores rank by lower anchor index (torch.topk leaves the order of ties unspecified). */
 size_t fvb_rpn_workspace_bytes(int batch, int height, int width, int anchors);
 int fvb_rpn_proposals_f32(const float* d_cls, const float* d_reg, const float* base_anchors, int batch,
                           int height, int width, int anchors, int pre_n, int post_n, double iou_thr,
-                          float* d_out_xywh, int32_t* d_out_cnt, void* d_ws, void* stream);
+                          float* d_out_xywh, int32_t* d_out_idx, int32_t* d_out_cnt, void* d_ws, void* stream);
 
 /* ---- K4 target assignment + loss ---------------------------------------------------------------
  * fvb_yolov3_loss_f32 replaces Yolov3Loss.forward, loss/yolov3_loss.py:29-72 (with build_target
  * :75-124, CIOULoss loss/iou_loss.py:83-107, BiCrossEntropyLoss loss/classification_loss.py:36-65).
- * d_labels [T,6] = [batch_idx, cls, xc, yc, w, h] normalised.  d_conf_bce0 = per-group zero-target
+ * d_labels [T,6] = [batch_idx, cls, xc, yc, w, h] normalised.  d_conf_bce0 = per-warp zero-target
  * objectness sums from fvb_yolo_decode_f32 over the same heads, or NULL (the call then streams
  * channel 4 itself).  d_partials [L*4] f64 receives per level {S_cls, S_box, S_conf, M}
  * (what a data-parallel run all-reduces).  If d_out_loss != NULL the scalar

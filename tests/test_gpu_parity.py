@@ -19,7 +19,7 @@ from fastvision_b200.detection import tools as ft
 from fastvision_b200.detection.models import yolov3_decode, DecodeContext
 from fastvision_b200 import loss as fl
 from fastvision_b200.metrics import CalculateMAP
-from fastvision_b200.pipeline import ValStep, shard_labels
+from fastvision_b200.pipeline import ValStep, ValPipeline, shard_labels
 
 
 def _heads(g, prefix="head"):
@@ -415,3 +415,35 @@ def test_full_size_properties_b256():
         p += lossf.partials
     close(p, out["partials"], rtol=1e-9, atol=0)
     close(lossf.combine(p, batch, ctx=step.ctx), out["loss"])
+
+
+def test_pipeline_overlapped_batches_match_serial_steps():
+    """ValPipeline (tail of batch i overlaps the decode of batch i+1, two buffer sets) == one ValStep per batch."""
+    cfg, batch = synth.COCO416, 6
+    batches = []
+    for r in range(5):
+        g = synth.make_generator(1, rank=10 + r)
+        labels = synth.make_labels(cfg, batch, g)
+        batches.append(([h.cuda() for h in synth.make_heads(cfg, batch, labels, g)], labels.cuda()))
+    ref = ValStep(cfg.anchors_levels(), cfg.strides)
+    want = []
+    for dh, dl in batches:
+        o = ref(dh, dl)
+        torch.cuda.synchronize()
+        want.append({k: v.clone() for k, v in o.items()})
+    pipe = ValPipeline(cfg.anchors_levels(), cfg.strides)
+    got = []
+    for i, (dh, dl) in enumerate(batches):
+        o = pipe.submit(dh, dl)
+        if i >= 1:                                   # read batch i-1 (still valid: its slot is reused at i+1)
+            pipe.wait((i - 1) % 2)
+            got.append({k: v.clone() for k, v in pipe.steps[(i - 1) % 2].out.items()})
+    pipe.flush()
+    got.append({k: v.clone() for k, v in o.items()})
+    torch.cuda.synchronize()
+    for w, g_ in zip(want, got):
+        assert torch.equal(w["results"], g_["results"]) and torch.equal(w["cnt"], g_["cnt"])
+        close(g_["loss"], w["loss"], rtol=1e-7, atol=0)
+        for i in range(batch):
+            k = int(w["cnt"][i])
+            assert torch.equal(w["boxes"][i, :k], g_["boxes"][i, :k]) and torch.equal(w["cls"][i, :k], g_["cls"][i, :k])

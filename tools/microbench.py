@@ -12,7 +12,7 @@ from fastvision_b200 import synth, _lib  # noqa: E402
 from fastvision_b200.detection.models import yolov3_decode, DecodeContext  # noqa: E402
 from fastvision_b200.detection.tools import non_max_suppression_batched  # noqa: E402
 from fastvision_b200.loss import Yolov3Loss  # noqa: E402
-from fastvision_b200.pipeline import ValStep  # noqa: E402
+from fastvision_b200.pipeline import ValStep, ValPipeline  # noqa: E402
 
 
 def timeit(fn, iters=20, warm=5):
@@ -79,6 +79,26 @@ def main():
     replay = step.capture(dh, dl)
     rep("step_graph", replay, bytes_alg)
     print("kept/img mean %.1f" % step.out["cnt"].float().mean().item(), "loss", step.out["loss"].item())
+    pipe = ValPipeline(anc, st)
+    for _ in range(5):
+        pipe.submit(dh, dl)
+    pipe.flush()
+    torch.cuda.synchronize()
+    for k in (50, 200):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            pipe.submit(dh, dl)
+        t_cpu = time.perf_counter() - t0
+        pipe.flush()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / k
+        out["step_pipelined_%d" % k] = {"ms_per_step": ms, "GBps": bytes_alg / ms / 1e6, "cpu_submit_ms": t_cpu / k * 1e3}
+        print("step_pipelined", k, out["step_pipelined_%d" % k], flush=True)
+    o = pipe.steps[(pipe.count - 1) % 2].out
+    print("pipelined kept/img mean %.1f" % o["cnt"].float().mean().item(), "loss", o["loss"].item())
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/microbench_%s_b%d%s.json" % (args.config, args.batch, "_stress" if args.stress else ""), "w") as f:
         json.dump(out, f, indent=1)
