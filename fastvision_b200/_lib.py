@@ -37,7 +37,8 @@ _SIGS = {
     "fvb_yolo_rows_per_image": (C.c_int, [C.POINTER(Geom)]),
     "fvb_yolo_bitmap_words": (C.c_int, [C.POINTER(Geom)]),
     "fvb_yolo_decode_partials": (C.c_int, [C.POINTER(Geom)]),
-    "fvb_yolo_decode_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), C.c_int, C.c_int, _P, C.c_float, _P, _P, _P, _P]),
+    "fvb_yolo_decode_workspace_bytes": (C.c_size_t, []),
+    "fvb_yolo_decode_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), C.c_int, C.c_int, _P, C.c_float, _P, _P, _P, _P, _P]),
     "fvb_box_convert_f32": (C.c_int, [_P, C.c_int64, C.c_int, C.c_float, C.c_float, _P, _P]),
     "fvb_iou_elementwise_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "fvb_iou_pairwise_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),

@@ -39,12 +39,12 @@ struct Geom {
 
 int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out);
 
-static const int kDecodeThreads = 512;
+static const int kDecodeThreads = 640;
 // Shared memory the persistent decode kernel may take per SM: leaves room for one NMS CTA (~112 KB) beside it.
 static const size_t kDecodeSmemBudget = 112 * 1024;
 
 // Launch shape of the decode kernel (decode.cu); also fixes the layout of the fused objectness-BCE partials:
-// [L][grid * warps_per_cta] doubles, one per warp of the grid and level.
+// one double per tile, level-major ([l][b][tile of the level]); tile = decode_tile_rows(K) rows of one segment.
 struct DecodeShape {
   int tile_rows, tile_floats;
   int tiles_level_end[FVB_MAX_LEVELS];
@@ -54,6 +54,7 @@ struct DecodeShape {
   size_t smem_bytes;
 };
 int decode_launch_shape(const Geom& g, DecodeShape* s);
+int decode_tile_rows(int K);
 
 // ---- device math, written to mirror torch's fp32 op order ------------------------------------------
 __device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }

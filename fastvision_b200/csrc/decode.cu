@@ -31,16 +31,19 @@ struct DecodeParams {
   int tile_rows;                        // T: rows per tile (16, 32, 64 or 128; wider rows -> fewer rows)
   int tiles_level_end[FVB_MAX_LEVELS];  // cumulative tiles per image, level by level
   int tiles_per_image;
-  long long total_tiles;
+  int total_tiles;
+  float inv_tpi;                        // 1/tiles_per_image, 1/HW, 1/W: seeds of the exact float divmod
+  float inv_hw[FVB_MAX_LEVELS], inv_w[FVB_MAX_LEVELS];
   int tile_floats;  // floats per shared-memory buffer (T*K rounded up to a multiple of 4)
   int warps_per_cta;
-  int stages;  // shared-memory buffers per warp: 1 (load, then process) or 2 (next tile in flight while processing)
   float* out;
   float conf_thr;
   uint32_t* bitmap;
   int bitmap_words;
   float* cand_rec;  // [B][N][8] = {row[0..3], conf, max_c(cls*conf), argmax as int bits, -}, written for candidates only
-  double* bce0;     // [L][NW]: zero-target objectness BCE partial of every warp of the grid, per level
+  double* bce0;     // one zero-target objectness BCE partial per tile, level-major: [l][b][tile of the level]
+  unsigned* sched;  // [0] next tile, [1] warps that have drained; both zero between launches
+  int batch_max;    // tiles drawn per atomic while the queue is long
 };
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
@@ -68,48 +71,91 @@ __device__ __forceinline__ float exp_dec(float t) {
   return ex2_approx(t * kLog2e);
 }
 
+// n / d and n % d for 0 <= n < 2^23, 1 <= d: float estimate (inv = 1.0f/d) corrected by at most one
+__device__ __forceinline__ void divmod_f(int n, int d, float inv, int& q, int& r) {
+  q = __float2int_rz(__int2float_rn(n) * inv);
+  r = n - q * d;
+  if (r < 0) {
+    q -= 1;
+    r += d;
+  } else if (r >= d) {
+    q += 1;
+    r -= d;
+  }
+}
+
 struct Tile {
   const float* src;  // first float of the run in the raw head
   float* dst;        // first float of the run in results
   size_t out_row;    // global row index (b*N + row_off[l] + row0)
   int n;             // floats in the run (nrows*K)
   int nrows, l, b, row0;
+  int part;          // index of this tile's objectness partial
 };
 
 __device__ __forceinline__ Tile describe_tile(const DecodeParams& p, int u) {
   Tile t;
-  const int b = u / p.tiles_per_image;
-  int r = u - b * p.tiles_per_image;
+  int b, r;
+  divmod_f(u, p.tiles_per_image, p.inv_tpi, b, r);
   int l = 0;
 #pragma unroll
   for (int i = 0; i < FVB_MAX_LEVELS - 1; ++i)
     if (i < p.g.L - 1 && r >= p.tiles_level_end[i]) l = i + 1;
-  if (l > 0) r -= p.tiles_level_end[l - 1];
+  const int lvl_first = l > 0 ? p.tiles_level_end[l - 1] : 0;
+  const int tiles_l = p.tiles_level_end[l] - lvl_first;
+  r -= lvl_first;
   const int rows_l = p.g.A * p.g.HW[l];
   t.row0 = r * p.tile_rows;
   t.nrows = min(p.tile_rows, rows_l - t.row0);
   t.n = t.nrows * p.g.K;
   t.l = l;
   t.b = b;
+  t.part = lvl_first * p.g.B + b * tiles_l + r;
   t.out_row = (size_t)b * p.g.row_off[p.g.L] + p.g.row_off[l] + t.row0;
   t.src = p.g.head[l] + ((size_t)b * rows_l + t.row0) * p.g.K;
   t.dst = p.out + t.out_row * p.g.K;
   return t;
 }
 
+// All flat loops below run `full` unguarded warp-wide steps (warp-uniform trip count: no divergence bookkeeping) and
+// one guarded remainder.
 __device__ __forceinline__ void issue_tile(const Tile& t, float* buf, int lane) {
   int done = 0;
   if ((reinterpret_cast<uintptr_t>(t.src) & 15) == 0) {
     const int n4 = t.n >> 2;
-    for (int i = lane; i < n4; i += 32) cp_async16(buf + 4 * i, t.src + 4 * i);
+    const float* s = t.src + 4 * lane;
+    float* d = buf + 4 * lane;
+    int k = n4 >> 5;
+#pragma unroll 1
+    for (; k >= 4; k -= 4, s += 512, d += 512) {
+      cp_async16(d, s);
+      cp_async16(d + 128, s + 128);
+      cp_async16(d + 256, s + 256);
+      cp_async16(d + 384, s + 384);
+    }
+#pragma unroll 1
+    for (; k > 0; --k, s += 128, d += 128) cp_async16(d, s);
+    if (lane < (n4 & 31)) cp_async16(d, s);
     done = n4 << 2;
+    if (done + lane < t.n) cp_async4(buf + done + lane, t.src + done + lane);
+    return;
   }
-  for (int i = done + lane; i < t.n; i += 32) cp_async4(buf + i, t.src + i);
+  const float* s = t.src + lane;
+  float* d = buf + lane;
+  int k = t.n >> 5;
+#pragma unroll 1
+  for (; k >= 8; k -= 8, s += 256, d += 256) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cp_async4(d + 32 * j, s + 32 * j);
+  }
+#pragma unroll 1
+  for (; k > 0; --k, s += 32, d += 32) cp_async4(d, s);
+  if (lane < (t.n & 31)) cp_async4(d, s);
 }
 
 // NSB = 32-row sub-blocks per tile (lane <-> row passes)
 template <int NSB, int FORM, bool PRECISE>
-__device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& t, float* buf, double (&acc)[FVB_MAX_LEVELS]) {
+__device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& t, float* buf) {
   const int lane = threadIdx.x & 31;
   const int K = p.g.K, l = t.l;
   const int W = p.g.W[l], HW = p.g.HW[l];
@@ -127,11 +173,9 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
       const float* sr = buf + r * K;
       t0 = sr[0]; t1 = sr[1]; t2 = sr[2]; t3 = sr[3]; t4 = sr[4];
     }
-    const int rl = t.row0 + (valid ? r : 0);
-    const int a = rl / HW;
-    const int yx = rl - a * HW;
-    const int y = yx / W;
-    const int x = yx - y * W;
+    int a, yx, y, x;
+    divmod_f(t.row0 + (valid ? r : 0), HW, p.inv_hw[l], a, yx);
+    divmod_f(yx, W, p.inv_w[l], y, x);
     const float aw = p.g.aw[l][a], ah = p.g.ah[l][a];
     const float s0 = sigmoid_dec<PRECISE>(t0), s1 = sigmoid_dec<PRECISE>(t1);
     conf[sb] = sigmoid_dec<PRECISE>(t4);
@@ -151,23 +195,48 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
     if (p.bce0 != nullptr && valid) bce += (double)bce_term_zero(conf[sb]);
   }
   if (p.bce0 != nullptr) {
-#pragma unroll
-    for (int i = 0; i < FVB_MAX_LEVELS; ++i) acc[i] += (i == l) ? bce : 0.0;  // per-lane fp64, reduced once at the end
+    bce = warp_sum(bce);  // fixed shuffle tree, one partial per tile: reproducible whichever warp runs the tile
+    if (lane == 0) p.bce0[t.part] = bce;
   }
   __syncwarp();
 
   // ---- A: flat in-place sigmoid ------------------------------------------------------------------------------------
   {
-    float4* b4 = reinterpret_cast<float4*>(buf);
     const int n4 = t.n >> 2;
-#pragma unroll 4
-    for (int i = lane; i < n4; i += 32) {
-      float4 v = b4[i];
-      v.x = sigmoid_dec<PRECISE>(v.x);
-      v.y = sigmoid_dec<PRECISE>(v.y);
-      v.z = sigmoid_dec<PRECISE>(v.z);
-      v.w = sigmoid_dec<PRECISE>(v.w);
-      b4[i] = v;
+    float4* q = reinterpret_cast<float4*>(buf) + lane;
+    int k = n4 >> 5;
+#pragma unroll 1
+    for (; k >= 4; k -= 4, q += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = q[32 * j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j].x = sigmoid_dec<PRECISE>(v[j].x);
+        v[j].y = sigmoid_dec<PRECISE>(v[j].y);
+        v[j].z = sigmoid_dec<PRECISE>(v[j].z);
+        v[j].w = sigmoid_dec<PRECISE>(v[j].w);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[32 * j] = v[j];
+    }
+    // <= 3 full steps + the ragged one, fused: at most 4 guarded vectors
+    {
+      const int rem = (k << 5) + (n4 & 31);  // vectors left, < 128
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j < rem) v[j] = q[32 * j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j].x = sigmoid_dec<PRECISE>(v[j].x);
+        v[j].y = sigmoid_dec<PRECISE>(v[j].y);
+        v[j].z = sigmoid_dec<PRECISE>(v[j].z);
+        v[j].w = sigmoid_dec<PRECISE>(v[j].w);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j < rem) q[32 * j] = v[j];
     }
     const int i = (n4 << 2) + lane;
     if (i < t.n) buf[i] = sigmoid_dec<PRECISE>(buf[i]);
@@ -183,17 +252,20 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
       float* sr = buf + r * K;
       sr[0] = ox[sb]; sr[1] = oy[sb]; sr[2] = ow[sb]; sr[3] = oh[sb]; sr[4] = conf[sb];
     }
+    __syncwarp();
     if (p.bitmap != nullptr && sb * 32 < t.nrows) {
       unsigned m = __ballot_sync(0xffffffffu, valid && conf[sb] > p.conf_thr);  // NMS.py:7 on the stored value
-      const unsigned gr = (unsigned)(p.g.row_off[l] + t.row0 + sb * 32);
-      const unsigned sh = gr & 31u;
-      uint32_t* wptr = p.bitmap + (size_t)t.b * p.bitmap_words + (gr >> 5);
-      if (lane == 0) {
-        const unsigned lo = m << sh;
-        if (lo) atomicOr(wptr, lo);
-      } else if (lane == 1 && sh) {
-        const unsigned hi = m >> (32u - sh);
-        if (hi) atomicOr(wptr + 1, hi);
+      if (m) {
+        const unsigned gr = (unsigned)(p.g.row_off[l] + t.row0 + sb * 32);
+        const unsigned sh = gr & 31u;
+        uint32_t* wptr = p.bitmap + (size_t)t.b * p.bitmap_words + (gr >> 5);
+        if (lane == 0) {
+          const unsigned lo = m << sh;
+          if (lo) atomicOr(wptr, lo);
+        } else if (lane == 1 && sh) {
+          const unsigned hi = m >> (32u - sh);
+          if (hi) atomicOr(wptr + 1, hi);
+        }
       }
       // candidate records: score = max_c(cls_c*conf) on the STORED fp32 values (NMS.py:13,16: first maximum on ties)
       if (p.cand_rec != nullptr) {
@@ -202,8 +274,6 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
           m &= m - 1;
           const float* row = buf + (sb * 32 + rr) * K;
           const float rconf = __shfl_sync(0xffffffffu, conf[sb], rr);
-          const float r0 = __shfl_sync(0xffffffffu, ox[sb], rr), r1 = __shfl_sync(0xffffffffu, oy[sb], rr);
-          const float r2 = __shfl_sync(0xffffffffu, ow[sb], rr), r3 = __shfl_sync(0xffffffffu, oh[sb], rr);
           // products of two sigmoids are >= +0, so their bit patterns order like unsigned integers
           unsigned best = 0u;
           int bidx = 0x7fffffff;
@@ -217,13 +287,8 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
           const unsigned wbest = __reduce_max_sync(0xffffffffu, best);
           const int widx = __reduce_min_sync(0xffffffffu, (best == wbest) ? bidx : 0x7fffffff);
           if (lane < 7) {
-            float val = r0;
-            val = lane == 1 ? r1 : val;
-            val = lane == 2 ? r2 : val;
-            val = lane == 3 ? r3 : val;
-            val = lane == 4 ? rconf : val;
-            val = lane == 5 ? __uint_as_float(wbest) : val;
-            val = lane == 6 ? __int_as_float(widx) : val;
+            // lanes 0..4: box + objectness, which B1 just stored into the tile row itself
+            const float val = lane < 5 ? row[lane] : (lane == 5 ? __uint_as_float(wbest) : __int_as_float(widx));
             p.cand_rec[(t.out_row + sb * 32 + rr) * 8 + lane] = val;
           }
         }
@@ -233,18 +298,41 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
   __syncwarp();
 
   // ---- copy-out: flat, coalesced ------------------------------------------------------------------------------------
-  {
-    int done = 0;
-    if ((reinterpret_cast<uintptr_t>(t.dst) & 15) == 0) {
-      const float4* b4 = reinterpret_cast<const float4*>(buf);
-      float4* d4 = reinterpret_cast<float4*>(t.dst);
-      const int n4 = t.n >> 2;
-#pragma unroll 4
-      for (int i = lane; i < n4; i += 32) d4[i] = b4[i];
-      done = n4 << 2;
+  if ((reinterpret_cast<uintptr_t>(t.dst) & 15) == 0) {
+    const int n4 = t.n >> 2;
+    const float4* q = reinterpret_cast<const float4*>(buf) + lane;
+    float4* d = reinterpret_cast<float4*>(t.dst) + lane;
+    int k = n4 >> 5;
+#pragma unroll 1
+    for (; k >= 4; k -= 4, q += 128, d += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = q[32 * j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[32 * j] = v[j];
     }
-#pragma unroll 8
-    for (int i = done + lane; i < t.n; i += 32) t.dst[i] = buf[i];
+    const int rem = (k << 5) + (n4 & 31);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (lane + 32 * j < rem) d[32 * j] = q[32 * j];
+    const int i = (n4 << 2) + lane;
+    if (i < t.n) t.dst[i] = buf[i];
+  } else {
+    const float* q = buf + lane;
+    float* d = t.dst + lane;
+    int k = t.n >> 5;
+#pragma unroll 1
+    for (; k >= 8; k -= 8, q += 256, d += 256) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = q[32 * j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[32 * j] = v[j];
+    }
+    const int rem = (k << 5) + (t.n & 31);  // < 256
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (lane + 32 * j < rem) d[32 * j] = q[32 * j];
   }
 }
 
@@ -252,55 +340,60 @@ template <int NSB, int FORM, bool PRECISE>
 __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const DecodeParams p) {
   extern __shared__ __align__(16) float dec_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* buf = dec_smem + (size_t)warp * p.stages * p.tile_floats;
-  const int nw = (int)gridDim.x * p.warps_per_cta;
-  const int gw = (int)blockIdx.x * p.warps_per_cta + warp;
-  const int total = (int)p.total_tiles;
-  double acc[FVB_MAX_LEVELS];
-#pragma unroll
-  for (int i = 0; i < FVB_MAX_LEVELS; ++i) acc[i] = 0.0;
-  if (p.stages == 1) {
-    for (int u = gw; u < total; u += nw) {
-      const Tile cur = describe_tile(p, u);
-      issue_tile(cur, buf, lane);
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncwarp();  // every lane's copies have landed
-      process_tile<NSB, FORM, PRECISE>(p, cur, buf, acc);
-      __syncwarp();  // the buffer may be refilled
+  float* buf = dec_smem + (size_t)warp * p.tile_floats;
+  const int total = p.total_tiles;
+  // dynamic tile queue: tiles are handed out in memory order to whichever warp is free, so a CTA that starts late or
+  // shares its SM with NMS CTAs of the previous batch simply takes fewer tiles.  A warp draws a BATCH of consecutive
+  // tiles per atomic (same-address atomics serialise in one L2 slice: one per tile costs more than the tile), and the
+  // batch shrinks towards the end of the queue (guided self-scheduling) so the tail stays one tile long.
+  const int nw = (int)(gridDim.x * (blockDim.x >> 5));
+  const int gmax = p.batch_max;
+  int u = 0, uend = 0;   // current batch [u, uend)
+  int nu = 0, nend = 0;  // prefetched next batch
+  int seen = 0;          // last ticket value seen: estimate of the queue position
+  {
+    if (lane == 0) nu = (int)atomicAdd(&p.sched[0], (unsigned)gmax);
+    nu = __shfl_sync(0xffffffffu, nu, 0);
+    nend = min(nu + gmax, total);
+    seen = nu;
+  }
+  bool have_next = true;
+  while (true) {
+    if (u >= uend) {
+      if (!have_next || nu >= total) break;
+      u = nu;
+      uend = nend;
+      have_next = false;
     }
-  } else {
-    int u = gw;
-    Tile cur, nxt;
-    cur.n = 0;
-    if (u < total) {
-      cur = describe_tile(p, u);
-      issue_tile(cur, buf, lane);
-    }
+    const Tile cur = describe_tile(p, u);
+    issue_tile(cur, buf, lane);
     cp_async_commit();
-    int stage = 0;
-    while (u < total) {
-      const int un = u + nw;
-      if (un < total) {
-        nxt = describe_tile(p, un);
-        issue_tile(nxt, buf + (stage ^ 1) * p.tile_floats, lane);
-      }
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncwarp();
-      process_tile<NSB, FORM, PRECISE>(p, cur, buf + stage * p.tile_floats, acc);
-      __syncwarp();
-      cur = nxt;
-      u = un;
-      stage ^= 1;
+    int t0 = 0, g = 1;
+    const bool fetch = !have_next && (u + 1 >= uend);  // on the last tile of the batch: draw the next batch now
+    if (fetch) {
+      const int rem = total - seen;
+      g = min(gmax, max(1, rem / (2 * nw)));
+      if (lane == 0) t0 = (int)atomicAdd(&p.sched[0], (unsigned)g);  // its latency hides behind this tile
     }
     cp_async_wait<0>();
+    __syncwarp();  // every lane's copies have landed
+    process_tile<NSB, FORM, PRECISE>(p, cur, buf);
+    __syncwarp();  // the buffer may be refilled
+    if (fetch) {
+      nu = __shfl_sync(0xffffffffu, t0, 0);
+      nend = min(nu + g, total);
+      seen = nu;
+      have_next = true;
+    }
+    ++u;
   }
-  if (p.bce0 != nullptr) {
-#pragma unroll
-    for (int i = 0; i < FVB_MAX_LEVELS; ++i) {
-      const double sum = warp_sum(acc[i]);
-      if (lane == 0 && i < p.g.L) p.bce0[(size_t)i * nw + gw] = sum;  // fixed tile -> warp map: reproducible
+  // the last warp to drain re-arms the queue for the next launch
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(&p.sched[1], 1u) == (unsigned)nw - 1u) {
+      p.sched[0] = 0u;
+      p.sched[1] = 0u;
+      __threadfence();
     }
   }
 }
@@ -324,10 +417,6 @@ int decode_launch_shape(const Geom& g, DecodeShape* s) {
     return FVB_E_CUDA;
   }
   s->tile_rows = decode_tile_rows(g.K);
-  {
-    const int tr = knob("FVB_DECODE_TILE_ROWS", 0, 0, 128);
-    if (tr == 8 || tr == 16 || tr == 32 || tr == 64 || tr == 128) s->tile_rows = tr;
-  }
   s->tile_floats = (s->tile_rows * g.K + 3) & ~3;
   int t = 0;
   for (int l = 0; l < g.L; ++l) {
@@ -341,8 +430,8 @@ int decode_launch_shape(const Geom& g, DecodeShape* s) {
     set_error("decode: %lld tiles", s->total_tiles);
     return FVB_E_LIMIT;
   }
-  s->stages = knob("FVB_DECODE_STAGES", 1, 1, 2);
-  const size_t per_warp = (size_t)s->stages * s->tile_floats * sizeof(float);
+  s->stages = 1;
+  const size_t per_warp = (size_t)s->tile_floats * sizeof(float);
   int wpc = (int)(kDecodeSmemBudget / per_warp);
   const int want = knob("FVB_DECODE_WARPS", kDecodeWarps, 1, kDecodeMaxThreads / 32);
   if (wpc > want) wpc = want;
@@ -433,16 +522,24 @@ extern "C" int fvb_yolo_bitmap_words(const fvb_yolo_geom* geom) {
 extern "C" int fvb_yolo_decode_partials(const fvb_yolo_geom* geom) {
   Geom g;
   if (make_geom(geom, nullptr, &g) != FVB_OK) return -1;
-  DecodeShape sh;
-  if (decode_launch_shape(g, &sh) != FVB_OK) return -1;
-  return g.L * sh.grid * sh.warps_per_cta;
+  long long t = 0;
+  const int tr = decode_tile_rows(g.K);
+  for (int l = 0; l < g.L; ++l) t += (g.A * g.HW[l] + tr - 1) / tr;
+  t *= g.B;
+  if (t >= (1ll << 23)) {
+    set_error("decode: %lld tiles (limit 2^23)", t);
+    return -1;
+  }
+  return (int)t;
 }
+
+extern "C" size_t fvb_yolo_decode_workspace_bytes(void) { return 256; }
 
 extern "C" int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
                                    float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
-                                   double* d_conf_bce0, void* stream) {
+                                   double* d_conf_bce0, void* d_ws, void* stream) {
   DecodeParams p;
-  FVB_REQUIRE(d_heads != nullptr && d_results != nullptr, "decode: NULL head/result pointer");
+  FVB_REQUIRE(d_heads != nullptr && d_results != nullptr && d_ws != nullptr, "decode: NULL head/result/workspace pointer");
   int rc = make_geom(geom, d_heads, &p.g);
   if (rc != FVB_OK) return rc;
   FVB_REQUIRE(form == FVB_DECODE_V3 || form == FVB_DECODE_V5, "decode: unknown form %d", form);
@@ -451,25 +548,35 @@ extern "C" int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const
     FVB_REQUIRE(d_heads[l] != nullptr, "decode: head %d is NULL", l);
     FVB_REQUIRE((reinterpret_cast<uintptr_t>(d_heads[l]) & 3) == 0, "decode: head %d is not 4-byte aligned", l);
   }
-  FVB_REQUIRE((reinterpret_cast<uintptr_t>(d_results) & 3) == 0, "decode: results not 4-byte aligned");
+  FVB_REQUIRE((reinterpret_cast<uintptr_t>(d_results) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_ws) & 7) == 0, "decode: results / workspace misaligned");
   FVB_REQUIRE(d_cand_rec == nullptr || d_cand_bitmap != nullptr, "decode: candidate records need the candidate bitmap too");
   if (p.g.B == 0) return FVB_OK;
   DecodeShape sh;
   rc = decode_launch_shape(p.g, &sh);
   if (rc != FVB_OK) return rc;
+  if (sh.total_tiles >= (1ll << 23)) {
+    set_error("decode: %lld tiles (limit 2^23)", sh.total_tiles);
+    return FVB_E_LIMIT;
+  }
   p.tile_rows = sh.tile_rows;
-  for (int l = 0; l < FVB_MAX_LEVELS; ++l) p.tiles_level_end[l] = sh.tiles_level_end[l];
+  for (int l = 0; l < FVB_MAX_LEVELS; ++l) {
+    p.tiles_level_end[l] = sh.tiles_level_end[l];
+    p.inv_hw[l] = l < p.g.L ? 1.0f / (float)p.g.HW[l] : 0.0f;
+    p.inv_w[l] = l < p.g.L ? 1.0f / (float)p.g.W[l] : 0.0f;
+  }
   p.tiles_per_image = sh.tiles_per_image;
-  p.total_tiles = sh.total_tiles;
+  p.total_tiles = (int)sh.total_tiles;
+  p.inv_tpi = 1.0f / (float)sh.tiles_per_image;
   p.tile_floats = sh.tile_floats;
   p.warps_per_cta = sh.warps_per_cta;
-  p.stages = sh.stages;
   p.out = d_results;
   p.conf_thr = conf_thr;
   p.bitmap = d_cand_bitmap;
   p.bitmap_words = (p.g.row_off[p.g.L] + 31) / 32;
   p.bce0 = d_conf_bce0;
   p.cand_rec = d_cand_rec;
+  p.sched = (unsigned*)d_ws;
+  p.batch_max = knob("FVB_DECODE_BATCH", 8, 1, 64);
   cudaStream_t s = (cudaStream_t)stream;
   if (form == FVB_DECODE_V3) rc = precise ? launch_decode<FVB_DECODE_V3, true>(p, sh, s) : launch_decode<FVB_DECODE_V3, false>(p, sh, s);
   else rc = precise ? launch_decode<FVB_DECODE_V5, true>(p, sh, s) : launch_decode<FVB_DECODE_V5, false>(p, sh, s);

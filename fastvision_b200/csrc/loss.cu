@@ -410,13 +410,12 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
   fp.batch_global = g.B;
   if (d_conf_bce0) {
     fp.conf0 = d_conf_bce0;
-    DecodeShape sh;
-    rc = decode_launch_shape(g, &sh);  // the decode kernel wrote one partial per warp of its grid and level
-    if (rc != FVB_OK) return rc;
-    const int nw = sh.grid * sh.warps_per_cta;
+    const int tr = decode_tile_rows(g.K);  // the decode kernel wrote one partial per tile, level-major
+    int t = 0;
     for (int l = 0; l < g.L; ++l) {
-      fp.level_begin[l] = l * nw;
-      fp.level_end[l] = (l + 1) * nw;
+      fp.level_begin[l] = t;
+      t += ((g.A * g.HW[l] + tr - 1) / tr) * g.B;
+      fp.level_end[l] = t;
     }
   } else {
     StreamParams sp;

@@ -31,7 +31,7 @@ class DecodeContext:
         if self.rows < 0:
             _lib.check(-1, "geometry")
         self.words = lib.fvb_yolo_bitmap_words(self.geom)
-        self._n_partials = None
+        self._sched = None
         self.device = h0.device
         self.key = (self.batch, self.num_anchors, self.k, tuple(self.heights), tuple(self.widths), self.device)
         self._bitmap = None
@@ -49,12 +49,17 @@ class DecodeContext:
             self._rec = torch.empty(self.batch, self.rows, 8, dtype=torch.float32, device=self.device)
         return self._rec
 
+    def sched(self):
+        """Tile queue of the persistent decode kernel: zero once, every launch leaves it zero (one per context)."""
+        if self._sched is None:
+            self._sched = torch.zeros(_lib.load().fvb_yolo_decode_workspace_bytes(), dtype=torch.uint8, device=self.device)
+        return self._sched
+
     def bce0(self):
         if self._bce0 is None:
-            with torch.cuda.device(self.device):      # the partial layout follows the decode grid of THIS device
-                n = _lib.load().fvb_yolo_decode_partials(self.geom)
+            n = _lib.load().fvb_yolo_decode_partials(self.geom)
             if n < 0:
-                _lib.check(-2, "decode_partials")
+                _lib.check(-3, "decode_partials")
             self._bce0 = torch.empty(n, dtype=torch.float64, device=self.device)
         return self._bce0
 
@@ -79,7 +84,8 @@ def yolov3_decode(head_out, anchors_per_level, strides, form="v3", precise=False
     with torch.cuda.device(ctx.device):
         _lib.check(lib.fvb_yolo_decode_f32(ctx.geom, _lib.head_ptrs(heads), _lib.DECODE_FORMS[form], 1 if precise else 0,
                                            _lib.dptr(out), float(conf_thres if conf_thres is not None else 0.0),
-                                           _lib.dptr(bitmap), _lib.dptr(rec), _lib.dptr(bce0), _lib.stream()),
+                                           _lib.dptr(bitmap), _lib.dptr(rec), _lib.dptr(bce0), _lib.dptr(ctx.sched()),
+                                           _lib.stream()),
                    "yolo_decode")
     return out
 

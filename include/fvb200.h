@@ -91,18 +91,20 @@ typedef struct {
  *                  {results[b,r,0..3], conf, max_c(cls_c*conf), argmax_c as int bits, unused} -- what
  *                  NMS.py:13-16 computes per candidate, produced while the row is in registers so the
  *                  NMS kernel never re-reads the 4*K-byte rows; non-candidate records are not written;
- *   d_conf_bce0    [fvb_yolo_decode_partials(geom)] f64: partial sums (one per warp of the decode grid and
- *                  level, fixed tile -> warp map, so reproducible) of -log(1 - sigmoid(t4) + 1e-8), the
- *                  zero-target part of the objectness BCE of Yolov3Loss (loss/yolov3_loss.py:63-64),
- *                  consumed by fvb_yolov3_loss_f32 on the same device.
+ *   d_conf_bce0    [fvb_yolo_decode_partials(geom)] f64: one partial sum per decode tile (fixed reduction tree,
+ *                  so reproducible) of -log(1 - conf + 1e-8), the zero-target part of the objectness BCE of
+ *                  Yolov3Loss (loss/yolov3_loss.py:63-64), consumed by fvb_yolov3_loss_f32.
+ * d_ws: fvb_yolo_decode_workspace_bytes() bytes (the tile queue of the persistent kernel), 8-byte aligned, ZERO
+ * before the first call; every launch leaves it zero again.  One workspace per concurrently running decode.
  * precise != 0 uses expf + IEEE division instead of ex2.approx/rcp.approx (both meet rtol 1e-5).
  */
 int fvb_yolo_rows_per_image(const fvb_yolo_geom* geom);
 int fvb_yolo_bitmap_words(const fvb_yolo_geom* geom);
-int fvb_yolo_decode_partials(const fvb_yolo_geom* geom); /* doubles in d_conf_bce0 (needs a CUDA device) */
+int fvb_yolo_decode_partials(const fvb_yolo_geom* geom); /* doubles in d_conf_bce0 */
+size_t fvb_yolo_decode_workspace_bytes(void);
 int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
                         float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
-                        double* d_conf_bce0, void* stream);
+                        double* d_conf_bce0, void* d_ws, void* stream);
 
 /* ---- box conversion ------------------------------------------------------------------------
  * detection/tools/BOX.py:4-26.  op: 0 xywh2xyxy, 1 xyxy2xywh, 2 xyxy2xywhn (needs height,width).

@@ -17,10 +17,10 @@ labels = synth.make_labels(cfg, batch, g)
 heads = [h.cuda() for h in synth.make_heads(cfg, batch, labels, g)]
 anc, st = cfg.anchors_levels(), cfg.strides
 rows = None
-for stages, warps, tr in [(1, 16, 0), (1, 18, 0), (1, 20, 0), (1, 16, 0), (1, 20, 0), (2, 10, 0), (1, 24, 8), (1, 20, 8)]:
-    os.environ["FVB_DECODE_STAGES"] = str(stages)
+for warps, gb in [(16, 8), (16, 1), (16, 4), (16, 16), (20, 8), (16, 8), (12, 8), (16, 2)]:
+    stages, tr = 1, gb
+    os.environ["FVB_DECODE_BATCH"] = str(gb)
     os.environ["FVB_DECODE_WARPS"] = str(warps)
-    os.environ["FVB_DECODE_TILE_ROWS"] = str(tr)
     ctx = DecodeContext(heads, anc, st)
     res = torch.empty(batch, ctx.rows, ctx.k, device="cuda")
     nbytes = 2 * batch * ctx.rows * ctx.k * 4
