@@ -26,6 +26,9 @@ struct LossParams {
   int T;
   double* match_ws;  // [L][blocks][4] = per-CTA sums of {S_cls, box term, conf correction, matched}
   int* flags;        // [0] labels grouped by image
+  const double* conf0;               // zero-target objectness partials (decode tiles or conf_stream chunks), level-major
+  int conf_begin[FVB_MAX_LEVELS];    // each level's contiguous range; CTA x of level l folds slice x of it into its sums
+  int conf_end[FVB_MAX_LEVELS];
 };
 
 __global__ void loss_prep_kernel(const float* labels, int T, int* flags) {
@@ -134,8 +137,9 @@ __global__ void __launch_bounds__(kLossThreads) loss_match_kernel(const LossPara
       const float ciou = iou_family<false>(pb, tb, FVB_CIOU, FVB_VARIANT_LIB, eps);
       const float iou = iou_plain<true>(pb, tb, eps);
       if (!loser) {
-        const float pc = sigmoid_precise(r4);
-        r_conf = (double)bce_term(pc, iou) - (double)bce_term(pc, 0.0f);
+        // the dense zero-target sum (decode tiles / conf_stream) holds bce(sigmoid_fast(t4), 0) for this cell: take
+        // exactly that back out and put the true term in
+        r_conf = (double)bce_term(sigmoid_precise(r4), iou) - (double)bce_term_zero(sigmoid_fast(r4));
       }
       r_cls = s_cls;
       r_box = (double)(1.0f - ciou);
@@ -148,11 +152,22 @@ __global__ void __launch_bounds__(kLossThreads) loss_match_kernel(const LossPara
     part[warp][2] = r_conf;
     part[warp][3] = r_m;
   }
-  __syncthreads();
+  // this CTA's slice of the level's dense objectness partials (fixed order: thread-strided, then the block tree)
+  __shared__ double scratch[32];
+  double cs = 0.0;
+  {
+    const int n = p.conf_end[l] - p.conf_begin[l];
+    const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int beg = p.conf_begin[l] + (int)blockIdx.x * per;
+    const int end = min(beg + per, p.conf_end[l]);
+    for (int i = beg + (int)threadIdx.x; i < end; i += kLossThreads) cs += p.conf0[i];
+  }
+  cs = block_sum(cs, scratch);  // syncs: part[] is complete too
   if (threadIdx.x < 4) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kLossThreads / 32; ++w) s += part[w][threadIdx.x];  // fixed order
+    if (threadIdx.x == 2) s += cs;  // block_sum leaves the total in every lane of warp 0
     p.match_ws[((size_t)l * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = s;
   }
 }
@@ -230,31 +245,37 @@ __device__ __forceinline__ double strided_sum(const double* v, int n) {
 __global__ void __launch_bounds__(1024) loss_finalize_kernel(const FinalizeParams p) {
   __shared__ double scratch[32];
   const int TA = p.match_blocks;
-  for (int l = 0; l < p.g.L; ++l) {
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    const double2* ws = reinterpret_cast<const double2*>(p.match_ws + (size_t)l * TA * 4);
-    int i = threadIdx.x;
-    for (; i + (int)blockDim.x < TA; i += 2 * blockDim.x) {
-      double2 u0 = ws[(size_t)i * 2], u1 = ws[(size_t)i * 2 + 1];
-      double2 w0 = ws[(size_t)(i + blockDim.x) * 2], w1 = ws[(size_t)(i + blockDim.x) * 2 + 1];
-      a0 += u0.x + w0.x; a1 += u0.y + w0.y; a2 += u1.x + w1.x; a3 += u1.y + w1.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (TA > 0) {
+    // loss_match already folded the dense objectness partials into its per-CTA sums: one warp per (level, component)
+    // walks that column in a fixed order -- no block barrier on the way
+    const int l = warp >> 2, c = warp & 3;
+    if (l < p.g.L) {
+      const double* ws = p.match_ws + (size_t)l * TA * 4 + c;
+      double s0 = 0.0, s1 = 0.0;
+      int i = lane;
+      for (; i + 32 < TA; i += 64) {
+        s0 += ws[(size_t)i * 4];
+        s1 += ws[(size_t)(i + 32) * 4];
+      }
+      if (i < TA) s0 += ws[(size_t)i * 4];
+      const double tot = warp_sum(s0 + s1);
+      if (lane == 0) p.partials[l * 4 + c] = tot;
     }
-    for (; i < TA; i += blockDim.x) {
-      double2 u0 = ws[(size_t)i * 2], u1 = ws[(size_t)i * 2 + 1];
-      a0 += u0.x; a1 += u0.y; a2 += u1.x; a3 += u1.y;
-    }
-    double c0 = strided_sum(p.conf0 + p.level_begin[l], p.level_end[l] - p.level_begin[l]);
-    a0 = block_sum(a0, scratch);
-    a1 = block_sum(a1, scratch);
-    a2 = block_sum(a2 + c0, scratch);
-    a3 = block_sum(a3, scratch);
-    if (threadIdx.x == 0) {
-      p.partials[l * 4 + 0] = a0;
-      p.partials[l * 4 + 1] = a1;
-      p.partials[l * 4 + 2] = a2;
-      p.partials[l * 4 + 3] = a3;
+  } else {
+    // no labels: only the objectness term exists (yolov3_loss.py:63-64)
+    for (int l = 0; l < p.g.L; ++l) {
+      double c0 = strided_sum(p.conf0 + p.level_begin[l], p.level_end[l] - p.level_begin[l]);
+      c0 = block_sum(c0, scratch);
+      if (threadIdx.x == 0) {
+        p.partials[l * 4 + 0] = 0.0;
+        p.partials[l * 4 + 1] = 0.0;
+        p.partials[l * 4 + 2] = c0;
+        p.partials[l * 4 + 3] = 0.0;
+      }
     }
   }
+  __threadfence_block();
   __syncthreads();
   if (threadIdx.x == 0 && p.out_loss != nullptr)
     p.out_loss[0] = combine_loss(p.g, p.partials, p.batch_global, p.r_box, p.r_conf, p.r_cls);
@@ -389,19 +410,8 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
   lp.labels = d_labels;
   lp.T = (int)num_labels;
 
-  const int wpb = kLossThreads / 32;
-  const int match_blocks = (int)(((long long)lp.T * g.A + wpb - 1) / wpb);
-  if (lp.T > 0) {
-    loss_prep_kernel<<<1, 1024, 0, s>>>(d_labels, lp.T, lp.flags);
-    dim3 grid((unsigned)match_blocks, (unsigned)g.L);
-    loss_match_kernel<<<grid, kLossThreads, 0, s>>>(lp);
-    count_launch(2);
-  }
-
   FinalizeParams fp;
   fp.g = g;
-  fp.match_blocks = match_blocks;
-  fp.match_ws = lp.match_ws;
   fp.partials = d_partials;
   fp.out_loss = d_out_loss;
   fp.r_box = ratio_box;
@@ -434,6 +444,22 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
     count_launch();
     fp.conf0 = stream_parts;
   }
+
+  const int wpb = kLossThreads / 32;
+  const int match_blocks = (int)(((long long)lp.T * g.A + wpb - 1) / wpb);
+  if (lp.T > 0) {
+    lp.conf0 = fp.conf0;
+    for (int l = 0; l < FVB_MAX_LEVELS; ++l) {
+      lp.conf_begin[l] = l < g.L ? fp.level_begin[l] : 0;
+      lp.conf_end[l] = l < g.L ? fp.level_end[l] : 0;
+    }
+    loss_prep_kernel<<<1, 1024, 0, s>>>(d_labels, lp.T, lp.flags);
+    dim3 grid((unsigned)match_blocks, (unsigned)g.L);
+    loss_match_kernel<<<grid, kLossThreads, 0, s>>>(lp);
+    count_launch(2);
+  }
+  fp.match_blocks = match_blocks;
+  fp.match_ws = lp.match_ws;
   loss_finalize_kernel<<<1, 1024, 0, s>>>(fp);
   count_launch();
   return check_launch("yolov3_loss");

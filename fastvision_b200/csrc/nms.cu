@@ -11,13 +11,20 @@
 //   2  block radix sort of (rank desc, slot asc) keys;
 //   3  chunked greedy suppression with a kept list (nms.cuh);
 //   4  padded outputs + count; consumed bitmap words are cleared for the next step.
-// Candidates live in shared memory up to kCapS per image; beyond that the same code runs on a
-// global workspace slice (slower, still exact) so there is no overflow case.
+// Candidates live in shared memory up to kCapS per image (keys, boxes, rows: 36 B each -- under 100 KB per CTA so
+// that TWO CTAs fit an SM and 256 images are one wave); beyond that the same code runs on a global workspace
+// slice (slower, still exact) so there is no overflow case.
 #include "nms.cuh"
 
 #include <math.h>
 
 namespace fvb {
+
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 constexpr int kCapS = 2048;  // candidates per image held in shared memory
 
@@ -40,13 +47,12 @@ struct YoloNmsParams {
   // global fallback, per image strides of N entries
   unsigned long long* ws_keys;  // [B][2][N]
   float4* ws_box;               // [B][N]
-  float* ws_score;              // [B][N]
-  int* ws_cat;                  // [B][N]
   int* ws_row;                  // [B][N]
+  long long* trace;             // debug: [B][8] clock64 stamps per phase (NULL in production)
 };
 
 struct NmsSmemLayout {
-  size_t keys0, keys1, box, score, cat, row, cnt, warp_tot, kbox, karea, kslot, gs, misc, total;
+  size_t keys0, keys1, box, row, cnt, warp_tot, kbox, karea, kslot, gs, misc, total;
 };
 
 __host__ __device__ inline NmsSmemLayout nms_layout(int cap, int max_keep) {
@@ -61,8 +67,6 @@ __host__ __device__ inline NmsSmemLayout nms_layout(int cap, int max_keep) {
   L.keys0 = take((size_t)cap * 8, 16);
   L.keys1 = take((size_t)cap * 8, 16);
   L.box = take((size_t)cap * 16, 16);
-  L.score = take((size_t)cap * 4, 16);
-  L.cat = take((size_t)cap * 4, 16);
   L.row = take((size_t)cap * 4, 16);
   L.cnt = take((size_t)kNmsWarps * 256 * 4, 16);
   L.warp_tot = take((size_t)(kNmsWarps + 1) * 4, 16);
@@ -89,6 +93,7 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
   int* misc = reinterpret_cast<int*>(smem + L.misc);  // [0] n_valid
 
   uint32_t* bm = p.bitmap + (size_t)b * p.words;
+  if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 0] = gtime_ns();
 
   // ---- phase 0: ordered candidate rows from the bitmap -------------------------------------------------
   const int wpt = (p.words + kNmsThreads - 1) / kNmsThreads;
@@ -101,21 +106,16 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
 
   unsigned long long *keys0, *keys1;
   float4* sbox;
-  float* sscore;
-  int *scat, *srow;
+  int* srow;
   if (n <= kCapS) {
     keys0 = reinterpret_cast<unsigned long long*>(smem + L.keys0);
     keys1 = reinterpret_cast<unsigned long long*>(smem + L.keys1);
     sbox = reinterpret_cast<float4*>(smem + L.box);
-    sscore = reinterpret_cast<float*>(smem + L.score);
-    scat = reinterpret_cast<int*>(smem + L.cat);
     srow = reinterpret_cast<int*>(smem + L.row);
   } else {
     keys0 = p.ws_keys + (size_t)b * 2 * p.N;
     keys1 = keys0 + p.N;
     sbox = p.ws_box + (size_t)b * p.N;
-    sscore = p.ws_score + (size_t)b * p.N;
-    scat = p.ws_cat + (size_t)b * p.N;
     srow = p.ws_row + (size_t)b * p.N;
   }
   {
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
     return;
   }
 
+  if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 1] = gtime_ns();
   // ---- phase 1: one thread per candidate, from its 32-byte record -----------------------------------------
   const float4* rec4 = reinterpret_cast<const float4*>(p.rec + (size_t)b * p.N * 8);
   int valid_local = 0;
@@ -161,8 +162,6 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
       bx.x1 += gap; bx.y1 += gap; bx.x2 += gap; bx.y2 += gap;
     }
     sbox[i] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
-    sscore[i] = rank;
-    scat[i] = bidx;
     const uint32_t hi = ok ? desc_key(rank) : 0xffffffffu;
     keys0[i] = ((unsigned long long)hi << 32) | (uint32_t)i;
     valid_local += ok ? 1 : 0;
@@ -173,14 +172,17 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
   const int n_use = min(misc[0], p.max_nms);
 
   // ---- phase 2 + 3 ---------------------------------------------------------------------------------------
+  if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 2] = gtime_ns();
   unsigned long long* sorted = block_radix_sort_hi32(keys0, keys1, n, cnt, warp_tot);
+  if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 3] = gtime_ns();
   int kept = block_greedy_nms(sorted, n_use, sbox, p.iou_thr, p.max_det, kbox, karea, kslot, gs);
+  if (p.trace && threadIdx.x == 0) { p.trace[b * 8 + 4] = gtime_ns(); p.trace[b * 8 + 6] = n; p.trace[b * 8 + 7] = kept; }
 
   // ---- phase 4: padded outputs -------------------------------------------------------------------------------
   for (int i = threadIdx.x; i < kept; i += kNmsThreads) {
     int slot = kslot[i];
     int r = srow[slot];
-    const float4 q0 = rec4[(size_t)r * 2];
+    const float4 q0 = rec4[(size_t)r * 2], q1 = rec4[(size_t)r * 2 + 1];  // score / class come back from the record
     Box bx;
     if (p.flavour == FVB_NMS_DEMO) {
       bx.x1 = q0.x; bx.y1 = q0.y; bx.x2 = q0.z; bx.y2 = q0.w;
@@ -189,11 +191,12 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
     }
     size_t o = (size_t)b * p.max_det + i;
     reinterpret_cast<float4*>(p.out_boxes)[o] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
-    p.out_scores[o] = sscore[slot];
-    p.out_cls[o] = (long long)scat[slot];
+    p.out_scores[o] = (p.flavour == FVB_NMS_DEMO) ? q1.x : q1.y;
+    p.out_cls[o] = (long long)__float_as_int(q1.z);
     if (p.out_rows) p.out_rows[o] = r;
   }
   if (threadIdx.x == 0) p.out_cnt[b] = kept;
+  if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 5] = gtime_ns();
 }
 
 // ---- stand-alone scoring: candidate bitmap + records straight from a decoded [B,N,K] tensor ------------------
@@ -331,14 +334,16 @@ static int ensure_smem(const void* fn, size_t bytes, const char* what) {
 
 using namespace fvb;
 
+static long long* g_nms_trace = nullptr;
+/* debug hook (tools/nms_trace.py): device buffer [B][8] of clock64 stamps written by yolo_nms_kernel; NULL disables */
+extern "C" void fvb_debug_set_nms_trace(void* d_buf) { g_nms_trace = (long long*)d_buf; }
+
 extern "C" size_t fvb_yolo_nms_workspace_bytes(int batch, int rows_per_image) {
   size_t bn = (size_t)batch * (size_t)rows_per_image;
   size_t words = ((size_t)rows_per_image + 31) / 32;
   size_t o = 0;
   o = align_up(o + bn * 2 * 8, 256);            // keys
   o = align_up(o + bn * 16, 256);               // boxes
-  o = align_up(o + bn * 4, 256);                // score
-  o = align_up(o + bn * 4, 256);                // cat
   o = align_up(o + bn * 4, 256);                // row
   o = align_up(o + (size_t)batch * words * 4, 256);  // private bitmap (stand-alone use)
   o = align_up(o + bn * 32, 256);                    // private candidate records (stand-alone use)
@@ -372,8 +377,6 @@ extern "C" int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_
   size_t o = 0;
   p.ws_keys = (unsigned long long*)(w + o); o = align_up(o + bn * 2 * 8, 256);
   p.ws_box = (float4*)(w + o);              o = align_up(o + bn * 16, 256);
-  p.ws_score = (float*)(w + o);             o = align_up(o + bn * 4, 256);
-  p.ws_cat = (int*)(w + o);                 o = align_up(o + bn * 4, 256);
   p.ws_row = (int*)(w + o);                 o = align_up(o + bn * 4, 256);
   FVB_REQUIRE((d_cand_bitmap == nullptr) == (d_cand_rec == nullptr), "yolo_nms: pass both the candidate bitmap and the records, or neither");
   cudaStream_t cs = (cudaStream_t)stream;
@@ -405,6 +408,7 @@ extern "C" int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_
   p.out_cls = (long long*)d_out_cls;
   p.out_rows = d_out_rows;
   p.out_cnt = d_out_cnt;
+  p.trace = g_nms_trace;
   NmsSmemLayout L = nms_layout(kCapS, max_det);
   int rc = ensure_smem((const void*)yolo_nms_kernel, L.total, "yolo_nms");
   if (rc != FVB_OK) return rc;

@@ -39,6 +39,32 @@ __device__ __forceinline__ bool nms_overlap(const float4& a, float area_a, const
   return inter / uni > thr;
 }
 
+// The same decision without the division for all but a sliver of pairs:  inter/(s - inter) > thr  <=>  inter > t*s
+// with t = thr/(1+thr), s = area_a + area_b (inter > 0 implies both areas and the union are positive).  `hit` is set
+// when inter clears the bound by 1e-5 (far beyond fp32 rounding of either form), `amb` when it is at least within
+// 1e-5 below it; a pair that is only `amb` must be re-decided with nms_overlap().  NaN boxes set neither.
+struct NmsFast {
+  float thi, tlo;
+  bool ok;  // thresholds outside (1e-6, 1e6) take the exact path only
+};
+__device__ __forceinline__ NmsFast make_nms_fast(float thr) {
+  NmsFast f;
+  f.ok = thr > 1e-6f && thr < 1e6f;
+  const float t = thr / (1.0f + thr);
+  f.thi = t * 1.00001f;
+  f.tlo = t * 0.99999f;
+  return f;
+}
+__device__ __forceinline__ void nms_overlap_fast(const float4& a, float area_a, const float4& b, float area_b,
+                                                 const NmsFast& f, bool& hit, bool& amb) {
+  const float w = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+  const float h = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+  const float inter = fmaxf(w, 0.0f) * fmaxf(h, 0.0f);
+  const float s = area_a + area_b;
+  hit |= inter > fmaxf(f.thi * s, 0.0f);
+  amb |= inter >= f.tlo * s;
+}
+
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_tot /*[kNmsWarps+1]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = v;
@@ -164,6 +190,7 @@ __device__ inline int block_greedy_nms(const unsigned long long* sorted, int n, 
                                 float4* kbox, float* karea, int* kslot, GreedyShared* gs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tid = threadIdx.x;
+  const NmsFast fast = make_nms_fast(thr);
   if (tid == 0) {
     gs->kcount = 0;
     const int cn0 = min(kNmsChunk, n);
@@ -178,7 +205,8 @@ __device__ inline int block_greedy_nms(const unsigned long long* sorted, int n, 
     const int kc = gs->kcount;
     if (kc >= max_keep) break;
     const int cn = min(kNmsChunk, n - c0);
-    // (a) against the kept list
+    // (a) against the kept list: branch-free fast decisions (two kept boxes in flight per step); a candidate that
+    // met a pair inside the guard band and no clear hit re-walks its slice with the exact test (rare)
     {
       const int r = tid & (kNmsChunk - 1), s = tid / kNmsChunk;
       constexpr int S = kNmsThreads / kNmsChunk;
@@ -186,10 +214,29 @@ __device__ inline int block_greedy_nms(const unsigned long long* sorted, int n, 
         const float4 bj = gs->cbox[buf][r];
         const float aj = gs->carea[buf][r];
         bool hit = false;
-        for (int i = s; i < kc; i += S) {
-          if (nms_overlap(kbox[i], karea[i], bj, aj, thr)) {
-            hit = true;
-            break;
+        if (fast.ok) {
+          bool amb = false;
+          int i = s;
+          for (; i + S < kc; i += 2 * S) {
+            const float4 k0 = kbox[i], k1 = kbox[i + S];
+            const float a0 = karea[i], a1 = karea[i + S];
+            nms_overlap_fast(k0, a0, bj, aj, fast, hit, amb);
+            nms_overlap_fast(k1, a1, bj, aj, fast, hit, amb);
+          }
+          if (i < kc) nms_overlap_fast(kbox[i], karea[i], bj, aj, fast, hit, amb);
+          if (amb && !hit) {
+            for (i = s; i < kc; i += S)
+              if (nms_overlap(kbox[i], karea[i], bj, aj, thr)) {
+                hit = true;
+                break;
+              }
+          }
+        } else {
+          for (int i = s; i < kc; i += S) {
+            if (nms_overlap(kbox[i], karea[i], bj, aj, thr)) {
+              hit = true;
+              break;
+            }
           }
         }
         if (hit) atomicAnd(&gs->alive32[r >> 5], ~(1u << (r & 31)));
@@ -204,7 +251,17 @@ __device__ inline int block_greedy_nms(const unsigned long long* sorted, int n, 
       for (int h = 0; h < kNmsChunk / 32; ++h) {
         const int q = h * 32 + lane;
         bool hit = false;
-        if (q > r && q < cn) hit = nms_overlap(br, ar, gs->cbox[buf][q], gs->carea[buf][q], thr);
+        if (q > r && q < cn) {
+          const float4 bq = gs->cbox[buf][q];
+          const float aq = gs->carea[buf][q];
+          if (fast.ok) {
+            bool amb = false;
+            nms_overlap_fast(br, ar, bq, aq, fast, hit, amb);
+            if (amb && !hit) hit = nms_overlap(br, ar, bq, aq, thr);
+          } else {
+            hit = nms_overlap(br, ar, bq, aq, thr);
+          }
+        }
         const unsigned w = __ballot_sync(0xffffffffu, hit);
         row |= (unsigned long long)w << (32 * h);
       }
