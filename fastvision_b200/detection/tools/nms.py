@@ -79,6 +79,23 @@ def non_max_suppression_batch(prediction_batch, conf_thres=0.25, iou_thres=0.45,
     return [out6[i, :cnt[i]] for i in range(len(cnt))]
 
 
+def non_max_suppression_frcnn(prediction, conf_thres=0.25, iou_thres=0.45, max_det=300, max_wh=4096, max_nms=30000):
+    """demos/faster_rcnn/utils/nms.py:5-39: rows [x1,y1,x2,y2,cat,score] -> the kept rows, score-descending.
+
+    The filter / gather glue stays torch indexing (as in the reference, one sync at the boolean mask); the
+    suppression itself is the segmented NMS kernel on gap-offset boxes (``box + cat*max_wh`` in fp32, :30-31).
+    """
+    pred = _lib.require_cuda(prediction, "prediction")
+    pred = pred[pred[:, 5] > conf_thres]                                    # :18
+    if pred.size(0) == 0:
+        return torch.zeros((0, 6), device=pred.device)
+    if pred.size(0) > max_nms:                                              # :23-24 (top by column 0, sic)
+        pred = pred[pred[:, 0].argsort(descending=True)[:max_nms]]
+    boxes = (pred[:, :4] + pred[:, 4:5] * max_wh).contiguous()
+    keep = nms(boxes, pred[:, 5].contiguous(), iou_thres, max_keep=max_det)
+    return pred[keep]
+
+
 def nms(boxes, scores, iou_threshold, seg_offsets=None, max_keep=None):
     """Batched ``torchvision.ops.nms``: kept indices, score-descending (ties: lower index first).
 

@@ -258,7 +258,30 @@ def gold_rpn(ns):
     np.savez_compressed(os.path.join(OUT, "rpn_small.npz"), **out)
 
 
+def gold_frcnn_nms(ns):
+    """demos/faster_rcnn/utils/nms.py:5-39 on clustered class-tagged detections -> tests/golden/frcnn_nms.npz."""
+    ref = ns.load_demo("faster_rcnn", "nms")
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    for tag, (n, ncls, thr, iou, md) in {"a": (400, 5, 0.25, 0.45, 300), "b": (60, 2, 0.5, 0.3, 10), "c": (32, 3, 0.99, 0.45, 300)}.items():
+        ctr = torch.rand(n // 4, 2, generator=g) * 300 + 50
+        ctr = ctr.repeat_interleave(4, 0) + torch.randn(n, 2, generator=g) * 6
+        wh = torch.rand(n, 2, generator=g) * 60 + 20
+        boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+        cat = torch.randint(0, ncls, (n, 1), generator=g).float()
+        score = torch.rand(n, 1, generator=g)
+        pred = torch.cat([boxes, cat, score], 1)
+        out[tag + "_pred"] = _np(pred)
+        out[tag + "_cfg"] = np.array([thr, iou, md], dtype=np.float64)
+        out[tag + "_out"] = _np(ref.non_max_suppression(pred, thr, iou, md))
+    np.savez_compressed(os.path.join(OUT, "frcnn_nms.npz"), **out)
+
+
 def main():
+    if "--only-frcnn-nms" in sys.argv:
+        torch.set_num_threads(1)
+        gold_frcnn_nms(ref_shim.load())
+        return
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ns = ref_shim.load()
@@ -267,6 +290,7 @@ def main():
     gold_tv_nms()
     gold_map(ns)
     gold_rpn(ns)
+    gold_frcnn_nms(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -114,3 +114,19 @@ def nms_demo_batch(prediction_batch, conf_thres=0.25, iou_thres=0.45, max_det=30
         k = _nms(p[:, :4] + gap, p[:, 4], iou_thres, backend)
         out[i] = p[k[:max_det]].detach().cpu()
     return out
+
+
+def nms_frcnn(prediction, conf_thres=0.25, iou_thres=0.45, max_det=300, backend="numpy", max_wh=4096, max_nms=30000):
+    """demos/faster_rcnn/utils/nms.py:5-39: rows [x1,y1,x2,y2,cat,score] -> kept rows (same 6 columns), score-descending.
+
+    Filter ``score > conf_thres`` (:18); more than ``max_nms`` rows keep the top by COLUMN 0 (sic, :24); class gap
+    ``cat * max_wh`` added in fp32 (:30-31); nms ranked by score (:33); first ``max_det`` (:34-35).
+    """
+    p = prediction[prediction[:, 5] > conf_thres]
+    if len(p) == 0:
+        return torch.zeros((0, 6), device=prediction.device)
+    if p.size(0) > max_nms:
+        p = p[p[:, 0].argsort(descending=True)[:max_nms]]
+    boxes = p[..., :4] + p[..., 4:5] * max_wh
+    k = _nms(boxes, p[..., 5], iou_thres, backend)
+    return p[k[:max_det]]

@@ -447,3 +447,14 @@ def test_pipeline_overlapped_batches_match_serial_steps():
         for i in range(batch):
             k = int(w["cnt"][i])
             assert torch.equal(w["boxes"][i, :k], g_["boxes"][i, :k]) and torch.equal(w["cls"][i, :k], g_["cls"][i, :k])
+
+
+def test_nms_frcnn_flavour_golden():
+    """demos/faster_rcnn/utils/nms.py:5-39 (class-tagged rows [x1,y1,x2,y2,cat,score])."""
+    from conftest import load_golden
+    g = load_golden("frcnn_nms.npz")
+    for tag in "abc":
+        thr, iou, md = g[tag + "_cfg"]
+        out = ft.non_max_suppression_frcnn(cuda(g[tag + "_pred"]), float(thr), float(iou), int(md))
+        assert tuple(out.shape) == g[tag + "_out"].shape, tag
+        assert np.array_equal(out.cpu().numpy(), g[tag + "_out"]), tag

@@ -189,3 +189,14 @@ def test_rpn(golden_rpn):
         props = oracle.rpn.filter_proposals(T(g[tag + "_cls"]), T(g[tag + "_reg"]), base, int(pre), int(post), float(thr))
         for i, p in enumerate(props):
             CLOSE(p, g["%s_prop%d" % (tag, i)])
+
+
+def test_nms_frcnn_flavour_vs_reference_golden():
+    """oracle.nms.nms_frcnn == demos/faster_rcnn/utils/nms.py:5-39 (recorded by oracle/make_golden.py gold_frcnn_nms)."""
+    from conftest import load_golden, T
+    from oracle import nms as on
+    g = load_golden("frcnn_nms.npz")
+    for tag in "abc":
+        thr, iou, md = g[tag + "_cfg"]
+        out = on.nms_frcnn(T(g[tag + "_pred"]), float(thr), float(iou), int(md))
+        assert np.array_equal(out.numpy(), g[tag + "_out"]), tag
