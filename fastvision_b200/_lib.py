@@ -15,6 +15,7 @@ BOX_MODES = {"xyxy": 0, "xywh": 1, "wh": 2}
 IOU_KINDS = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3}
 VARIANTS = {"lib": 0, "demo": 1}
 DECODE_FORMS = {"v3": 0, "v5": 1}
+HEAD_LAYOUTS = {"bahwk": 0, "nchw": 1}
 NMS_FLAVOURS = {"lib": 0, "demo": 1, "demo_batch": 2}
 REDUCTIONS = {"mean": 0, "sum": 1}
 
@@ -26,6 +27,7 @@ class Geom(C.Structure):
         ("stride", C.c_float * MAX_LEVELS),
         ("anchor_w", (C.c_float * MAX_ANCHORS) * MAX_LEVELS),
         ("anchor_h", (C.c_float * MAX_ANCHORS) * MAX_LEVELS),
+        ("head_layout", C.c_int32),
     ]
 
 
@@ -120,7 +122,7 @@ def require_cuda(t, name, dtype=torch.float32):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def make_geom(batch, channels, heights, widths, strides, anchors_per_level):
+def make_geom(batch, channels, heights, widths, strides, anchors_per_level, head_layout="bahwk"):
     """anchors_per_level: list (per level) of [A,2]-shaped (w,h) pixel anchors (tensor / list)."""
     g = Geom()
     levels = len(heights)
@@ -143,6 +145,7 @@ def make_geom(batch, channels, heights, widths, strides, anchors_per_level):
             g.anchor_w[l][i] = float(w)
             g.anchor_h[l][i] = float(h)
     g.anchors = na or 0
+    g.head_layout = HEAD_LAYOUTS[head_layout]
     return g
 
 

@@ -35,6 +35,7 @@ struct Geom {
   float aw[FVB_MAX_LEVELS][FVB_MAX_ANCHORS];  // pixels
   float ah[FVB_MAX_LEVELS][FVB_MAX_ANCHORS];
   const float* head[FVB_MAX_LEVELS];
+  int nchw;  // heads are [B,A*K,H,W] (decode only)
 };
 
 int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out);

@@ -153,6 +153,39 @@ __device__ __forceinline__ void issue_tile(const Tile& t, float* buf, int lane) 
   if (lane < (t.n & 31)) cp_async4(d, s);
 }
 
+// NCHW heads ([B, A*K, H, W], the conv output): the tile's rows are T consecutive cells of one anchor plane stack,
+// channel k of row r lives HW floats after channel k-1.  Lanes <-> (row, channel phase): every instruction reads
+// runs of min(T,32) consecutive cells (64-128 contiguous bytes) of 32/min(T,32) channels and drops them transposed
+// into the row-major tile, which the rest of the pipeline then treats exactly like the [B,A,H,W,K] case.
+template <int NSB>
+__device__ __forceinline__ void issue_tile_nchw(const DecodeParams& p, const Tile& t, float* buf, int lane) {
+  const int K = p.g.K, l = t.l, HW = p.g.HW[l];
+  const int ri = p.tile_rows < 32 ? p.tile_rows : 32;  // rows per instruction (power of two)
+  const int kl = 32 / ri;                              // channels per instruction
+  const int r_in = lane & (ri - 1), kk = lane / ri;
+#pragma unroll
+  for (int sb = 0; sb < NSB; ++sb) {
+    const int r = sb * 32 + r_in;
+    if (r < t.nrows) {
+      int a, pos;
+      divmod_f(t.row0 + r, HW, p.inv_hw[l], a, pos);
+      const float* s = p.g.head[l] + ((size_t)(t.b * p.g.A + a) * K + kk) * HW + pos;
+      float* d = buf + r * K + kk;
+      const size_t step = (size_t)kl * HW;
+      int k = kk;
+#pragma unroll 1
+      for (; k + 3 * kl < K; k += 4 * kl, s += 4 * step, d += 4 * kl) {
+        cp_async4(d, s);
+        cp_async4(d + kl, s + step);
+        cp_async4(d + 2 * kl, s + 2 * step);
+        cp_async4(d + 3 * kl, s + 3 * step);
+      }
+#pragma unroll 1
+      for (; k < K; k += kl, s += step, d += kl) cp_async4(d, s);
+    }
+  }
+}
+
 // NSB = 32-row sub-blocks per tile (lane <-> row passes)
 template <int NSB, int FORM, bool PRECISE>
 __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& t, float* buf) {
@@ -366,7 +399,8 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
       have_next = false;
     }
     const Tile cur = describe_tile(p, u);
-    issue_tile(cur, buf, lane);
+    if (p.g.nchw) issue_tile_nchw<NSB>(p, cur, buf, lane);
+    else issue_tile(cur, buf, lane);
     cp_async_commit();
     int t0 = 0, g = 1;
     const bool fetch = !have_next && (u + 1 >= uend);  // on the last tile of the batch: draw the next batch now
@@ -483,6 +517,8 @@ int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out) {
     return FVB_E_LIMIT;
   }
   out->row_off[g->levels] = (int)rows;
+  FVB_REQUIRE(g->head_layout == FVB_HEAD_BAHWK || g->head_layout == FVB_HEAD_NCHW, "unknown head_layout %d", g->head_layout);
+  out->nchw = g->head_layout == FVB_HEAD_NCHW;
   return FVB_OK;
 }
 

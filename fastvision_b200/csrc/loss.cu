@@ -399,6 +399,7 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
   if (rc != FVB_OK) return rc;
   for (int l = 0; l < lp.g.L; ++l) FVB_REQUIRE(d_heads[l] != nullptr, "yolov3_loss: head %d is NULL", l);
   FVB_REQUIRE(lp.g.B >= 1, "yolov3_loss: empty batch");
+  FVB_REQUIRE(!lp.g.nchw, "yolov3_loss: heads must be [B,A,H,W,K] (FVB_HEAD_BAHWK)");
   const Geom& g = lp.g;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned char* w = (unsigned char*)d_ws;

@@ -17,15 +17,32 @@ class DecodeContext:
     so that a steady-state step allocates nothing.
     """
 
-    def __init__(self, head_out, anchors_per_level, strides):
+    def __init__(self, head_out, anchors_per_level, strides, layout="bahwk"):
         h0 = head_out[0]
-        self.batch, self.num_anchors, _, _, self.k = h0.shape
-        self.heights = [int(h.size(2)) for h in head_out]
-        self.widths = [int(h.size(3)) for h in head_out]
-        for h in head_out:
-            if h.dim() != 5 or h.size(0) != self.batch or h.size(1) != self.num_anchors or h.size(4) != self.k:
-                raise ValueError("head tensors must all be [B,A,H,W,K]; got %s" % [tuple(x.shape) for x in head_out])
-        self.geom = _lib.make_geom(self.batch, self.k, self.heights, self.widths, strides, anchors_per_level)
+        self.layout = layout
+        if layout == "nchw":
+            # the conv output [B, A*K, H, W] itself (channel a*K + k): the head's permute().contiguous() copy
+            # (detection/head/yolov3head.py:61-63) is folded into the decode kernel's loads
+            a0 = anchors_per_level[0]
+            self.num_anchors = int(a0.numel() // 2) if isinstance(a0, torch.Tensor) else len(a0)
+            if h0.dim() != 4 or h0.size(1) % self.num_anchors:
+                raise ValueError("nchw head tensors must be [B, A*K, H, W] with A=%d; got %s" % (self.num_anchors, tuple(h0.shape)))
+            self.batch, self.k = h0.size(0), h0.size(1) // self.num_anchors
+            self.heights = [int(h.size(2)) for h in head_out]
+            self.widths = [int(h.size(3)) for h in head_out]
+            for h in head_out:
+                if h.dim() != 4 or h.size(0) != self.batch or h.size(1) != self.num_anchors * self.k:
+                    raise ValueError("head tensors must all be [B,A*K,H,W]; got %s" % [tuple(x.shape) for x in head_out])
+        elif layout == "bahwk":
+            self.batch, self.num_anchors, _, _, self.k = h0.shape
+            self.heights = [int(h.size(2)) for h in head_out]
+            self.widths = [int(h.size(3)) for h in head_out]
+            for h in head_out:
+                if h.dim() != 5 or h.size(0) != self.batch or h.size(1) != self.num_anchors or h.size(4) != self.k:
+                    raise ValueError("head tensors must all be [B,A,H,W,K]; got %s" % [tuple(x.shape) for x in head_out])
+        else:
+            raise ValueError("layout must be 'bahwk' or 'nchw'")
+        self.geom = _lib.make_geom(self.batch, self.k, self.heights, self.widths, strides, anchors_per_level, layout)
         lib = _lib.load()
         self.rows = lib.fvb_yolo_rows_per_image(self.geom)
         if self.rows < 0:
@@ -34,6 +51,8 @@ class DecodeContext:
         self._sched = None
         self.device = h0.device
         self.key = (self.batch, self.num_anchors, self.k, tuple(self.heights), tuple(self.widths), self.device)
+        if layout != "bahwk":
+            self.key = self.key + (layout,)
         self._bitmap = None
         self._bce0 = None
         self._rec = None
@@ -65,8 +84,13 @@ class DecodeContext:
 
 
 def yolov3_decode(head_out, anchors_per_level, strides, form="v3", precise=False, ctx=None, out=None,
-                  conf_thres=None, want_bce0=False):
+                  conf_thres=None, want_bce0=False, layout="bahwk", row_order="ayx"):
     """Decode raw heads (list of [B,A,H,W,K]) into ``results`` [B,N,K]  (yolov3.py:36-51).
+
+    ``layout="nchw"`` takes the conv outputs [B,A*K,H,W] directly (demos/yolov3_huaweiShip/customize_service.py:437).
+    ``row_order="yxa"`` returns each level's rows in (y, x, a) order -- the order of the demos' single-image
+    ``postProcess`` (demos/yolov3_huaweiShip/inference.py:107, view [B,H,W,A,K]); that is a permuted view-copy of
+    the kernel's (a, y, x) result and drops the fused NMS side outputs' row numbering, so use it only for that API.
 
     With ``conf_thres`` the kernel also fills ``ctx.bitmap()`` / ``ctx.records()`` (NMS candidates and their
     score / class / box records); with ``want_bce0`` it fills ``ctx.bce0()`` (zero-target objectness BCE
@@ -74,7 +98,7 @@ def yolov3_decode(head_out, anchors_per_level, strides, form="v3", precise=False
     """
     heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
     if ctx is None:
-        ctx = DecodeContext(heads, anchors_per_level, strides)
+        ctx = DecodeContext(heads, anchors_per_level, strides, layout)
     if out is None:
         out = torch.empty(ctx.batch, ctx.rows, ctx.k, dtype=torch.float32, device=ctx.device)
     lib = _lib.load()
@@ -87,6 +111,15 @@ def yolov3_decode(head_out, anchors_per_level, strides, form="v3", precise=False
                                            _lib.dptr(bitmap), _lib.dptr(rec), _lib.dptr(bce0), _lib.dptr(ctx.sched()),
                                            _lib.stream()),
                    "yolo_decode")
+    if row_order == "yxa":
+        parts, r0 = [], 0
+        for h, w in zip(ctx.heights, ctx.widths):
+            n = ctx.num_anchors * h * w
+            parts.append(out[:, r0:r0 + n].view(ctx.batch, ctx.num_anchors, h * w, ctx.k).permute(0, 2, 1, 3).reshape(ctx.batch, n, ctx.k))
+            r0 += n
+        return torch.cat(parts, 1)
+    if row_order != "ayx":
+        raise ValueError("row_order must be 'ayx' or 'yxa'")
     return out
 
 

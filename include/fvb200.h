@@ -65,6 +65,11 @@ const char* fvb_last_error(void);
 /* Number of kernel launches this process has enqueued through the library (bench.py: gpu_launches). */
 uint64_t fvb_launch_count(void);
 
+/* raw head layouts */
+#define FVB_HEAD_BAHWK 0 /* [B,A,H,W,K] contiguous, detection/head/yolov3head.py:63 (what Yolov3.forward decodes) */
+#define FVB_HEAD_NCHW 1  /* [B,A*K,H,W] contiguous: the conv output itself, channel a*K+k (demos/yolov3_huaweiShip/inference.py:107,
+                            customize_service.py:437) -- decode only; the loss entry points need FVB_HEAD_BAHWK */
+
 /* Geometry of a YOLO head stack, host memory.  Level order = concat order (stride 32,16,8). */
 typedef struct {
   int32_t levels;   /* L <= FVB_MAX_LEVELS */
@@ -76,12 +81,14 @@ typedef struct {
   float stride[FVB_MAX_LEVELS];
   float anchor_w[FVB_MAX_LEVELS][FVB_MAX_ANCHORS]; /* pixels */
   float anchor_h[FVB_MAX_LEVELS][FVB_MAX_ANCHORS];
+  int32_t head_layout; /* FVB_HEAD_* */
 } fvb_yolo_geom;
 
 /* ---- K1 decode ---------------------------------------------------------------------------
  * Replaces the decode block of Yolov3.forward, detection/models/yolov3.py:33-53 (and the demo
- * forms, demos/yolov3_u/inference.py:86-89).  d_heads[l] is the contiguous [B,A,H_l,W_l,K] raw
- * head tensor of level l (detection/head/yolov3head.py:63); d_results is [B,N,K] with
+ * forms, demos/yolov3_u/inference.py:86-89).  d_heads[l] is the contiguous raw head tensor of level l in
+ * geom->head_layout ([B,A,H_l,W_l,K], detection/head/yolov3head.py:63, or the conv output [B,A*K,H_l,W_l] whose
+ * permute().contiguous() copy the kernel then saves); d_results is [B,N,K] with
  * N = A*sum(H_l*W_l), row a*H*W + y*W + x inside a level.
  * Optional fused side outputs (either may be NULL):
  *   d_cand_bitmap  [B, fvb_yolo_bitmap_words(geom)] u32, must be zero on entry: bit r of image b

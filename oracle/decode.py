@@ -33,3 +33,32 @@ def decode(head_out, anchors_per_level, strides, form="v3"):
         dec = torch.cat((xy, wh, raw[..., 4:].sigmoid()), -1)
         results.append(dec.view(bs, -1, k))
     return torch.cat(results, 1)
+
+
+def decode_demo_nchw(predict_layers, anchors_feat_levels, strides, order="yxa"):
+    """The demos' decode of the raw NCHW conv outputs, batch kept (no un-letterbox): list of [B, A*K, H, W] ->
+    [B, N, K].  ``order="yxa"`` restates demos/yolov3_huaweiShip/inference.py:107-117 (permute(0,2,3,1).view(bs,h,w,A,K),
+    rows (y,x,a)); ``order="ayx"`` restates customize_service.py:437-447 (view(bs,A,K,h,w).permute(0,1,3,4,2), rows
+    (a,y,x)).  Anchors are in FEATURE units and re-multiplied by the stride: wh = (exp(t) * a_feat) * stride.
+    """
+    outs = []
+    for lvl, predict in enumerate(predict_layers):
+        anchor = anchors_feat_levels[lvl].view(-1, 2)
+        na = anchor.size(0)
+        stride = strides[lvl]
+        bs, c, h, w = predict.shape
+        ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        cell = torch.stack([xs, ys], -1).to(predict)                                       # [H,W,2] = (x, y)
+        if order == "yxa":
+            p = predict.permute(0, 2, 3, 1).reshape(bs, h, w, na, -1).clone()
+            g = cell.view(1, h, w, 1, 2)
+            a = anchor.view(1, 1, 1, na, 2)
+        else:
+            p = predict.view(bs, na, c // na, h, w).permute(0, 1, 3, 4, 2).contiguous().clone()
+            g = cell.view(1, 1, h, w, 2)
+            a = anchor.view(1, na, 1, 1, 2)
+        p[..., 0:2] = (torch.sigmoid(p[..., 0:2]) + g) * stride
+        p[..., 2:4] = (torch.exp(p[..., 2:4]) * a) * stride
+        p[..., 4:] = torch.sigmoid(p[..., 4:])
+        outs.append(p.reshape(bs, -1, c // na))
+    return torch.cat(outs, 1)

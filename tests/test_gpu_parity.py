@@ -458,3 +458,25 @@ def test_nms_frcnn_flavour_golden():
         out = ft.non_max_suppression_frcnn(cuda(g[tag + "_pred"]), float(thr), float(iou), int(md))
         assert tuple(out.shape) == g[tag + "_out"].shape, tag
         assert np.array_equal(out.cpu().numpy(), g[tag + "_out"]), tag
+
+
+@pytest.mark.parametrize("cfg,batch", [(synth.COCO416, 5), (synth.SHIP608, 3)])
+def test_decode_nchw_heads(cfg, batch):
+    """SURVEY 8 a1': the conv outputs [B,A*K,H,W] decoded directly == decoding their permuted copies (bitwise), and
+    == the demos' own formulation (feature-unit anchors x stride; (a,y,x) and (y,x,a) row orders) to rtol 1e-5."""
+    g = synth.make_generator(3, rank=7)
+    labels = synth.make_labels(cfg, batch, g)
+    heads = synth.make_heads(cfg, batch, labels, g)                               # [B,A,H,W,K]
+    nchw = [h.permute(0, 1, 4, 2, 3).reshape(h.size(0), -1, h.size(2), h.size(3)).contiguous() for h in heads]
+    anc, st = cfg.anchors_levels(), cfg.strides
+    want = yolov3_decode([h.cuda() for h in heads], anc, st)
+    ctx = DecodeContext([h.cuda() for h in nchw], anc, st, layout="nchw")
+    got = yolov3_decode([h.cuda() for h in nchw], anc, st, layout="nchw", ctx=ctx, conf_thres=0.25, want_bce0=True)
+    assert torch.equal(got, want)
+    ctx0 = DecodeContext([h.cuda() for h in heads], anc, st)
+    yolov3_decode([h.cuda() for h in heads], anc, st, ctx=ctx0, conf_thres=0.25, want_bce0=True)
+    assert torch.equal(ctx.bitmap(), ctx0.bitmap()) and torch.equal(ctx.bce0(), ctx0.bce0())
+    anc_feat = [a.view(-1, 2) / s for a, s in zip(anc, st)]
+    close(got, oracle.decode.decode_demo_nchw(nchw, anc_feat, st, order="ayx"))
+    got_yxa = yolov3_decode([h.cuda() for h in nchw], anc, st, layout="nchw", row_order="yxa")
+    close(got_yxa, oracle.decode.decode_demo_nchw(nchw, anc_feat, st, order="yxa"))
