@@ -57,8 +57,11 @@ struct DecodeShape {
 int decode_launch_shape(const Geom& g, DecodeShape* s);
 int decode_tile_rows(int K);
 
+// host+device for the pure arithmetic: tests/host_check.cu runs the same source on the CPU (no GPU in the build container)
+#define FVB_HD __host__ __device__ __forceinline__
+
 // ---- device math, written to mirror torch's fp32 op order ------------------------------------------
-__device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+FVB_HD float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // MUFU forms used by the streaming kernels: <= 2.5e-6 relative to torch's sigmoid for |x| <= 30
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -75,14 +78,14 @@ constexpr float kLog2e = 1.4426950408889634f;
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(x * -kLog2e)); }
 
 // -t*log(p+1e-8) - (1-t)*log(1-p+1e-8), loss/classification_loss.py:55, evaluated exactly in that form.
-__device__ __forceinline__ float bce_term(float p, float t) {
+FVB_HD float bce_term(float p, float t) {
   float a = (-t) * logf(p + 1e-8f);
   float b = (1.0f - t) * logf((1.0f - p) + 1e-8f);
   return a - b;
 }
 
 // The same expression with t = 0: the first product is (-0)*finite = +-0, so the result is exactly 0 - 1*log(...).
-__device__ __forceinline__ float bce_term_zero(float p) { return 0.0f - logf((1.0f - p) + 1e-8f); }
+FVB_HD float bce_term_zero(float p) { return 0.0f - logf((1.0f - p) + 1e-8f); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -116,7 +119,7 @@ struct Box {
   float x1, y1, x2, y2;
 };
 
-__device__ __forceinline__ Box xywh_to_xyxy(float x, float y, float w, float h) {
+FVB_HD Box xywh_to_xyxy(float x, float y, float w, float h) {
   // detection/tools/BOX.py:4-10: divide by 2, then subtract/add
   float hw = w / 2.0f, hh = h / 2.0f;
   Box b;
@@ -127,9 +130,9 @@ __device__ __forceinline__ Box xywh_to_xyxy(float x, float y, float w, float h) 
   return b;
 }
 
-__device__ __forceinline__ float clamp0(float z) { return fmaxf(z, 0.0f); }
+FVB_HD float clamp0(float z) { return fmaxf(z, 0.0f); }
 
-__device__ __forceinline__ float inter_area(const Box& a, const Box& b) {
+FVB_HD float inter_area(const Box& a, const Box& b) {
   float iw = clamp0(fminf(a.x2, b.x2) - fmaxf(a.x1, b.x1));
   float ih = clamp0(fminf(a.y2, b.y2) - fmaxf(a.y1, b.y1));
   return iw * ih;
@@ -140,7 +143,7 @@ __device__ __forceinline__ float inter_area(const Box& a, const Box& b) {
 
 // inner_eps: element-wise xyxy_iou puts eps inside the height factor (IOU.py:74-75); pairwise does not (:143-144)
 template <bool INNER_EPS>
-__device__ __forceinline__ float iou_plain(const Box& a, const Box& b, float eps, float* union_out = nullptr) {
+FVB_HD float iou_plain(const Box& a, const Box& b, float eps, float* union_out = nullptr) {
   float area_a, area_b;
   if (INNER_EPS) {
     area_a = (a.x2 - a.x1) * ((a.y2 - a.y1) + eps);
@@ -157,7 +160,7 @@ __device__ __forceinline__ float iou_plain(const Box& a, const Box& b, float eps
 
 // kind in {IOU,GIOU,DIOU,CIOU}; PAIRWISE selects the *_batch arithmetic of the reference.
 template <bool PAIRWISE>
-__device__ __forceinline__ float iou_family(const Box& a, const Box& b, int kind, int variant, float eps) {
+FVB_HD float iou_family(const Box& a, const Box& b, int kind, int variant, float eps) {
   if (kind == FVB_IOU) return iou_plain<!PAIRWISE>(a, b, eps);
   float cw = fmaxf(a.x2, b.x2) - fminf(a.x1, b.x1);
   float ch = fmaxf(a.y2, b.y2) - fminf(a.y1, b.y1);
@@ -193,6 +196,20 @@ __device__ __forceinline__ float iou_family(const Box& a, const Box& b, int kind
   float v = four_over_pi2 * (d * d);
   float alpha = v / ((v - iou) + (1.0f + eps));  // 1 + eps is folded in double, then to fp32 (IOU.py:437)
   return diou - alpha * v;
+}
+
+FVB_HD Box load_box(const float* p, int box_mode) {
+  if (box_mode == FVB_BOX_XYWH) return xywh_to_xyxy(p[0], p[1], p[2], p[3]);
+  Box b;
+  b.x1 = p[0]; b.y1 = p[1]; b.x2 = p[2]; b.y2 = p[3];
+  return b;
+}
+
+// wh_iou: detection/tools/IOU.py:108-120 / :177-189
+FVB_HD float wh_iou(float w1, float h1, float w2, float h2, float eps) {
+  float inter = fminf(w1, w2) * fminf(h1, h2);
+  float uni = ((w1 * h1 + w2 * h2) - inter) + eps;
+  return inter / uni;
 }
 
 }  // namespace fvb

@@ -6,20 +6,6 @@
 
 namespace fvb {
 
-__device__ __forceinline__ Box load_box(const float* p, int box_mode) {
-  if (box_mode == FVB_BOX_XYWH) return xywh_to_xyxy(p[0], p[1], p[2], p[3]);
-  Box b;
-  b.x1 = p[0]; b.y1 = p[1]; b.x2 = p[2]; b.y2 = p[3];
-  return b;
-}
-
-// wh_iou: detection/tools/IOU.py:108-120 / :177-189
-__device__ __forceinline__ float wh_iou(float w1, float h1, float w2, float h2, float eps) {
-  float inter = fminf(w1, w2) * fminf(h1, h2);
-  float uni = ((w1 * h1 + w2 * h2) - inter) + eps;
-  return inter / uni;
-}
-
 __global__ void iou_elementwise_kernel(const float* a, const float* b, long long n, int box_mode, int kind, int variant,
                                        float eps, float* out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -12,19 +12,19 @@ struct BoxGrad {
   float x1, y1, x2, y2;
 };
 
-__device__ __forceinline__ BoxGrad zero_grad() {
+FVB_HD BoxGrad zero_grad() {
   BoxGrad g;
   g.x1 = g.y1 = g.x2 = g.y2 = 0.0f;
   return g;
 }
 
 // d min(a,b): share of the incoming gradient that goes to `a` (torch.minimum backward)
-__device__ __forceinline__ float min_share(float a, float b) { return a < b ? 1.0f : (a == b ? 0.5f : 0.0f); }
-__device__ __forceinline__ float max_share(float a, float b) { return a > b ? 1.0f : (a == b ? 0.5f : 0.0f); }
+FVB_HD float min_share(float a, float b) { return a < b ? 1.0f : (a == b ? 0.5f : 0.0f); }
+FVB_HD float max_share(float a, float b) { return a > b ? 1.0f : (a == b ? 0.5f : 0.0f); }
 
 // plain IoU (inner_eps as in iou_plain); returns iou, accumulates g * d iou / d box into ga, gb
 template <bool INNER_EPS>
-__device__ __forceinline__ float iou_plain_grad(const Box& a, const Box& b, float eps, float g, BoxGrad& ga, BoxGrad& gb,
+FVB_HD float iou_plain_grad(const Box& a, const Box& b, float eps, float g, BoxGrad& ga, BoxGrad& gb,
                                                 float* union_out = nullptr, float g_union_extra = 0.0f) {
   const float wa = a.x2 - a.x1, ha = a.y2 - a.y1, wb = b.x2 - b.x1, hb = b.y2 - b.y1;
   const float hae = INNER_EPS ? ha + eps : ha, hbe = INNER_EPS ? hb + eps : hb;
@@ -61,7 +61,7 @@ __device__ __forceinline__ float iou_plain_grad(const Box& a, const Box& b, floa
 }
 
 // Element form of the family: returns the value and ACCUMULATES g * d value / d box into ga, gb.
-__device__ __forceinline__ float iou_family_grad(const Box& a, const Box& b, int kind, int variant, float eps, float g,
+FVB_HD float iou_family_grad(const Box& a, const Box& b, int kind, int variant, float eps, float g,
                                                  BoxGrad& ga, BoxGrad& gb) {
   if (kind == FVB_IOU) return iou_plain_grad<true>(a, b, eps, g, ga, gb);
   const float cw = fmaxf(a.x2, b.x2) - fminf(a.x1, b.x1);
@@ -143,7 +143,7 @@ __device__ __forceinline__ float iou_family_grad(const Box& a, const Box& b, int
 }
 
 // chain an xyxy gradient back through xywh_to_xyxy (BOX.py:4-10): x1 = x - w/2, x2 = x + w/2
-__device__ __forceinline__ void xyxy_grad_to_xywh(const BoxGrad& g, float* gx, float* gy, float* gw, float* gh) {
+FVB_HD void xyxy_grad_to_xywh(const BoxGrad& g, float* gx, float* gy, float* gw, float* gh) {
   *gx = g.x1 + g.x2;
   *gy = g.y1 + g.y2;
   *gw = (g.x2 - g.x1) / 2.0f;

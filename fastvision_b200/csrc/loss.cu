@@ -14,6 +14,7 @@
 // The objectness sum is  sum_cells bce(p,0) + sum_winners (bce(p,iou) - bce(p,0)) : the first part
 // is a pure stream, the second touches only matched rows.
 #include "common.cuh"
+#include "loss_common.cuh"
 
 namespace fvb {
 
@@ -39,36 +40,6 @@ __global__ void loss_prep_kernel(const float* labels, int T, int* flags) {
     if ((int)labels[(size_t)t * 6] > (int)labels[(size_t)(t + 1) * 6]) bad = 1;
   __syncthreads();
   if (threadIdx.x == 0) flags[0] = bad ? 0 : 1;
-}
-
-struct TargetCell {
-  bool match;
-  int b, cls, gx, gy;
-  float offx, offy, tw, th, aw, ah;
-};
-
-// build_target for one (target, anchor) on one level: loss/yolov3_loss.py:88-117.
-__device__ __forceinline__ TargetCell target_cell(const Geom& g, int l, const float* lab, int a) {
-  TargetCell c;
-  const int W = g.W[l], H = g.H[l];
-  const float fw = (float)W, fh = (float)H;
-  const float tx = lab[2] * fw, ty = lab[3] * fh;  // :94-95  y_true[:, 2:] * [W,H,W,H]
-  c.tw = lab[4] * fw;
-  c.th = lab[5] * fh;
-  c.aw = g.aw[l][a] / g.stride[l];  // :88-89 anchors in feature units
-  c.ah = g.ah[l][a] / g.stride[l];
-  const float rw = c.tw / c.aw, rh = c.th / c.ah;  // :98
-  const float m = fmaxf(fmaxf(rw, 1.0f / rw), fmaxf(rh, 1.0f / rh));
-  c.match = m < 4.0f;  // :99
-  c.b = (int)lab[0];
-  c.cls = (int)lab[1];
-  const float fx = floorf(tx), fy = floorf(ty);  // :113
-  c.offx = tx - fx;                              // :114 (before the clamp)
-  c.offy = ty - fy;
-  // clamp in float first so that a huge coordinate cannot overflow the int conversion
-  c.gx = (int)fminf(fmaxf(fx, 0.0f), (float)(W - 1));  // :116
-  c.gy = (int)fminf(fmaxf(fy, 0.0f), (float)(H - 1));  // :117
-  return c;
 }
 
 __global__ void __launch_bounds__(kLossThreads) loss_match_kernel(const LossParams p) {

@@ -1,8 +1,41 @@
-"""Binary cross-entropy -- drop-in for BiCrossEntropyLoss, loss/classification_loss.py:36-65."""
+"""Binary cross-entropy -- drop-in for BiCrossEntropyLoss, loss/classification_loss.py:36-65 (forward + backward w.r.t. y_pre)."""
 import torch
 import torch.nn as nn
 
 from .. import _lib
+
+
+def _forward(y_pre, tidx, tval, weights, rows, classes, sig, red):
+    out = torch.empty((), dtype=torch.float32, device=y_pre.device)
+    lib = _lib.load()
+    ws = _lib.workspace(lib.fvb_reduce_workspace_bytes(y_pre.numel()), y_pre.device, "reduce")
+    with torch.cuda.device(y_pre.device):
+        _lib.check(lib.fvb_bce_loss_f32(_lib.dptr(y_pre), rows, classes, _lib.dptr(tidx), _lib.dptr(tval), sig,
+                                        _lib.dptr(weights), _lib.REDUCTIONS[red], _lib.dptr(out), _lib.dptr(ws),
+                                        _lib.stream()), "bce_loss")
+    return out
+
+
+class _BCEFn(torch.autograd.Function):
+
+    @staticmethod
+    def forward(fctx, y_pre, tidx, tval, weights, rows, classes, sig, red):
+        fctx.save_for_backward(y_pre, tidx, tval, weights)
+        fctx.cfg = (rows, classes, sig, red)
+        return _forward(y_pre, tidx, tval, weights, rows, classes, sig, red)
+
+    @staticmethod
+    def backward(fctx, grad_out):
+        y_pre, tidx, tval, weights = fctx.saved_tensors
+        rows, classes, sig, red = fctx.cfg
+        g = torch.empty_like(y_pre)
+        grad_out = _lib.require_cuda(grad_out.detach().reshape(-1)[:1], "grad_out")
+        lib = _lib.load()
+        with torch.cuda.device(y_pre.device):
+            _lib.check(lib.fvb_bce_loss_backward_f32(_lib.dptr(y_pre), rows, classes, _lib.dptr(tidx), _lib.dptr(tval), sig,
+                                                     _lib.dptr(weights), _lib.REDUCTIONS[red], _lib.dptr(grad_out), _lib.dptr(g),
+                                                     _lib.stream()), "bce_loss_backward")
+        return g, None, None, None, None, None, None, None
 
 
 class BiCrossEntropyLoss(nn.Module):
@@ -28,12 +61,8 @@ class BiCrossEntropyLoss(nn.Module):
             weights = _lib.require_cuda(weights, "weights")
             if weights.numel() != y_pre.numel():
                 raise ValueError("weights must match the flattened prediction")
-        out = torch.empty((), dtype=torch.float32, device=y_pre.device)
-        lib = _lib.load()
-        ws = _lib.workspace(lib.fvb_reduce_workspace_bytes(y_pre.numel()), y_pre.device, "reduce")
-        red = _lib.REDUCTIONS["mean" if self.reduction == 'mean' else "sum"]
-        with torch.cuda.device(y_pre.device):
-            _lib.check(lib.fvb_bce_loss_f32(_lib.dptr(y_pre), rows, classes, _lib.dptr(tidx), _lib.dptr(tval),
-                                            1 if already_sigmoid else 0, _lib.dptr(weights), red, _lib.dptr(out),
-                                            _lib.dptr(ws), _lib.stream()), "bce_loss")
-        return out
+        red = "mean" if self.reduction == 'mean' else "sum"
+        sig = 1 if already_sigmoid else 0
+        if torch.is_grad_enabled() and y_pre.requires_grad:
+            return _BCEFn.apply(y_pre, tidx, tval, None if weights is None else weights.detach(), rows, classes, sig, red)
+        return _forward(y_pre, tidx, tval, weights, rows, classes, sig, red)

@@ -1,15 +1,37 @@
-"""YOLOv3 loss -- drop-in for Yolov3Loss, loss/yolov3_loss.py:8-124 (forward only this round).
+"""YOLOv3 loss -- drop-in for Yolov3Loss, loss/yolov3_loss.py:8-124, forward and backward.
 
 ``forward(y_pred, y_true)`` returns Tensor[1] exactly like the reference; the ~200 ATen launches and
 >=6 host syncs collapse into 3-4 small kernels.  ``partials`` ([L,4] f64: S_cls, S_box, S_conf, M per
 level) is what a data-parallel run all-reduces; ``combine`` turns reduced partials into the
 scalar with the global-batch normalisers.
+
+When a head tensor requires grad the call goes through ``_Yolov3LossFn``: ``loss.backward()`` (utils/fit.py:57-63) then runs
+``fvb_yolov3_loss_backward_f32`` -- one streaming kernel that writes the whole gradient of the three head tensors plus one
+small kernel for the matched rows -- instead of autograd's ~400 backward launches through the reference graph.
 """
 import torch
 import torch.nn as nn
 
 from .. import _lib
 from ..detection.models.yolov3 import DecodeContext
+
+
+class _Yolov3LossFn(torch.autograd.Function):
+    """autograd bridge: forward = fvb_yolov3_loss_f32, backward = fvb_yolov3_loss_backward_f32."""
+
+    @staticmethod
+    def forward(fctx, module, labels, geom_ctx, conf_bce0, out, partials, batch_global, *heads):
+        loss = module._forward_impl(list(heads), labels, geom_ctx, conf_bce0, out, partials)
+        fctx.module, fctx.geom_ctx, fctx.labels = module, geom_ctx, labels
+        fctx.partials, fctx.batch_global = module.partials, batch_global
+        fctx.save_for_backward(*heads)
+        return loss
+
+    @staticmethod
+    def backward(fctx, grad_out):
+        heads = fctx.saved_tensors
+        grads = fctx.module.backward_heads(list(heads), fctx.labels, grad_out, fctx.partials, fctx.batch_global, ctx=fctx.geom_ctx)
+        return (None, None, None, None, None, None, None) + tuple(grads)
 
 
 class Yolov3Loss(nn.Module):
@@ -44,6 +66,11 @@ class Yolov3Loss(nn.Module):
         heads = [_lib.require_cuda(h, "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
         labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
         ctx = ctx or self._context(heads)
+        if torch.is_grad_enabled() and any(h.requires_grad for h in heads):
+            return _Yolov3LossFn.apply(self, labels.detach(), ctx, conf_bce0, out, partials, None, *heads)
+        return self._forward_impl(heads, labels, ctx, conf_bce0, out, partials)
+
+    def _forward_impl(self, heads, labels, ctx, conf_bce0, out, partials):
         dev = ctx.device
         t = labels.size(0)
         if out is None:
@@ -59,6 +86,33 @@ class Yolov3Loss(nn.Module):
                                                _lib.dptr(ws), _lib.stream()), "yolov3_loss")
         self.partials = partials
         return out
+
+    def backward_heads(self, y_pred, y_true, grad_out=None, partials=None, batch_global=None, ctx=None, grads=None):
+        """Gradients of ``forward`` w.r.t. the raw head tensors (list of [B,A,H,W,K], written completely).
+
+        ``partials``: the forward's [L,4] partials (all-reduced under data parallelism, together with ``batch_global``);
+        ``grad_out``: the upstream gradient (Tensor[1] on the device) or None for 1.
+        """
+        heads = [_lib.require_cuda(h.detach(), "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
+        labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
+        ctx = ctx or self._context(heads)
+        dev = ctx.device
+        partials = self.partials if partials is None else partials
+        if partials is None:
+            raise RuntimeError("backward_heads needs the forward's partials (call forward first)")
+        if grads is None:
+            grads = [torch.empty_like(h) for h in heads]
+        if grad_out is not None:
+            grad_out = _lib.require_cuda(grad_out.detach().reshape(-1)[:1], "grad_out")
+        lib = _lib.load()
+        ws = _lib.workspace(lib.fvb_yolov3_loss_backward_workspace_bytes(), dev, "yolov3_loss_bwd")
+        bg = int(batch_global) if batch_global else int(heads[0].size(0))
+        with torch.cuda.device(dev):
+            _lib.check(lib.fvb_yolov3_loss_backward_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), labels.size(0),
+                                                        float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
+                                                        bg, _lib.dptr(partials), _lib.dptr(grad_out), _lib.head_ptrs(grads),
+                                                        _lib.dptr(ws), _lib.stream()), "yolov3_loss_backward")
+        return grads
 
     def combine(self, partials, batch_global, ctx=None, out=None):
         """Scalar loss from (all-reduced) per-level partials with GLOBAL-batch normalisers."""

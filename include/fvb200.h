@@ -206,6 +206,32 @@ int fvb_yolov3_build_target_f32(const fvb_yolo_geom* geom, int level, const floa
                                 float* d_xywh, float* d_anchor, uint8_t* d_match, int32_t* d_count,
                                 void* stream);
 
+/* ---- K4' backward (what loss.backward() in Fit._train, utils/fit.py:57-63, makes autograd do) ---------
+ * fvb_yolov3_loss_backward_f32: gradients of Yolov3Loss.forward (loss/yolov3_loss.py:29-72) w.r.t. the raw head
+ * tensors.  d_grad_heads[l] has the layout of d_heads[l] ([B,A,H,W,K]) and is written completely (no pre-zeroing):
+ * channel 4 of every cell gets the objectness-BCE gradient (:63-64), matched rows additionally get the class-BCE
+ * (:50-52), CIoU (:54-58, alpha constant as in detection/tools/IOU.py:436-437) and IoU-target (:60-61, the reference
+ * does not detach targets_conf) gradients; duplicate matches of one cell accumulate as torch's index / index_put
+ * backward do.  d_partials: the [L*4] f64 partials of the forward (M_l at [l*4+3]; all-reduced under data
+ * parallelism, with batch_global the global batch).  d_grad_out: device scalar [1] (the upstream gradient) or NULL
+ * for 1.  d_ws: fvb_yolov3_loss_backward_workspace_bytes() bytes.  Bit-reproducible (one writer per row, no atomics).
+ */
+size_t fvb_yolov3_loss_backward_workspace_bytes(void);
+int fvb_yolov3_loss_backward_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                 int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                                 int64_t batch_global, const double* d_partials, const float* d_grad_out,
+                                 float* const* d_grad_heads, void* d_ws, void* stream);
+/* Gradients of fvb_iou_loss_f32 (loss/iou_loss.py:5-107) w.r.t. y_pre and/or y_true (either output may be NULL);
+ * same box_mode layout as the inputs ([n,4], or [n,2] for wh).  torch conventions: minimum/maximum split ties 1/2,
+ * clamp(0) passes the gradient at 0.  d_ws: >= 256 bytes. */
+int fvb_iou_loss_backward_f32(const float* d_pre, const float* d_true, const float* d_weights, int64_t n, int box_mode,
+                              int kind, int variant, float eps, int reduction, const float* d_grad_out,
+                              float* d_grad_pre, float* d_grad_true, void* d_ws, void* stream);
+/* Gradient of fvb_bce_loss_f32 (loss/classification_loss.py:36-65) w.r.t. y_pre, [rows, C]. */
+int fvb_bce_loss_backward_f32(const float* d_pre, int64_t rows, int classes, const int64_t* d_target_idx,
+                              const float* d_target_val, int already_sigmoid, const float* d_weights, int reduction,
+                              const float* d_grad_out, float* d_grad_pre, void* stream);
+
 /* ---- K5 mAP matcher ----------------------------------------------------------------------------
  * CalculateMAP.process_one, metrics/map.py:16-83, for I images in one launch.  d_dets [sum M,6] =
  * [cls, conf, x1,y1,x2,y2], d_det_off [I+1]; d_gts [sum N,5] = [cls, x1,y1,x2,y2], d_gt_off [I+1];

@@ -170,7 +170,8 @@ def CIOU(b1, b2, mode="xyxy", eps=1e-7, variant="lib"):
     w2, h2 = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
     v = (4 / math.pi ** 2) * torch.pow(torch.atan(w2 / (h2 + eps)) - torch.atan(w1 / (h1 + eps)), 2)
     v = v.view(-1, 1)
-    alpha = v / (v - iou + (1 + eps))
+    with torch.no_grad():                                  # IOU.py:436-437: alpha is a constant for autograd
+        alpha = v / (v - iou + (1 + eps))
     return diou - alpha * v
 
 
@@ -182,7 +183,8 @@ def CIOU_batch(b1, b2, mode="xyxy", eps=1e-7, variant="lib"):
     w1, h1 = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]
     w2, h2 = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
     v = (4 / math.pi ** 2) * torch.pow(torch.atan(w1 / (h1 + eps))[:, None] - torch.atan(w2 / (h2 + eps)), 2)
-    alpha = v / (v - iou + (1 + eps))
+    with torch.no_grad():                                  # IOU.py:478-479
+        alpha = v / (v - iou + (1 + eps))
     return diou - alpha * v
 
 

@@ -277,10 +277,86 @@ def gold_frcnn_nms(ns):
     np.savez_compressed(os.path.join(OUT, "frcnn_nms.npz"), **out)
 
 
+def gold_grads(ns):
+    """Gradients recorded from the reference's own autograd graph (what loss.backward() in utils/fit.py:57-63 computes):
+    Yolov3Loss w.r.t. the three raw head tensors (duplicate cell, clamped cell, unmatched label included), the four IoU
+    losses w.r.t. y_pre / y_true in both box modes, and BiCrossEntropyLoss w.r.t. its logits -> tests/golden/grads_small.npz."""
+    out = {}
+    labels, heads = small_case(7)
+    extra = torch.tensor([[0, 1, 1.0, 0.5, 0.3, 0.4],
+                          [1, 2, 0.26, 0.26, 0.3, 0.35],
+                          [1, 3, 0.27, 0.27, 0.32, 0.33],
+                          [1, 1, 0.265, 0.262, 0.31, 0.36],
+                          [2, 0, 0.5, 0.5, 0.001, 0.001]], dtype=torch.float32)
+    labels = torch.cat([labels, extra], 0)
+    anc = SMALL.anchors_levels()
+
+    class Model:
+        anchors_per_level = anc
+        backbone_strides_per_level = SMALL.strides
+
+    lossf = ns.Yolov3Loss(Model(), 0.5, 0.05, 1.0, 0.5)
+    out["labels"] = _np(labels)
+    hs = [h.clone().requires_grad_(True) for h in heads]
+    loss = lossf(hs, labels)
+    (loss * 1.7).sum().backward()                      # a non-unit upstream gradient
+    out["loss"] = _np(loss)
+    out["upstream"] = np.float32(1.7)
+    for i, h in enumerate(hs):
+        out["head%d" % i] = _np(heads[i])
+        out["grad%d" % i] = _np(h.grad)
+    hs = [h.clone().requires_grad_(True) for h in heads]
+    lossf(hs, labels[:0]).sum().backward()
+    for i, h in enumerate(hs):
+        out["grad_nolabels%d" % i] = _np(h.grad)
+    # IoU losses
+    g = torch.Generator().manual_seed(21)
+    n = 48
+    a = rand_boxes_xyxy(n, g, degenerate=False)
+    b = rand_boxes_xyxy(n, g, degenerate=False)
+    b[:24] = a[:24] + torch.randn(24, 4, generator=g) * 3.0
+    t = ns.tools
+    aw, bw = t.xyxy2xywh(a), t.xyxy2xywh(b)
+    w = torch.rand(n, 1, generator=g)
+    out["a"], out["b"], out["a_xywh"], out["b_xywh"], out["w"] = _np(a), _np(b), _np(aw), _np(bw), _np(w)
+    for name, cls in [("iou", ns.loss.IOULoss), ("giou", ns.loss.GIOULoss), ("diou", ns.loss.DIOULoss), ("ciou", ns.loss.CIOULoss)]:
+        for tag, (x, y, mode, red, ww) in {"xyxy_mean": (a, b, "xyxy", "mean", None), "xywh_sum": (aw, bw, "xywh", "sum", None),
+                                           "xyxy_mean_w": (a, b, "xyxy", "mean", w)}.items():
+            xx, yy = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+            cls(red)(xx, yy, weights=ww, mode=mode).backward()
+            out["g_%s_%s_pre" % (name, tag)] = _np(xx.grad)
+            out["g_%s_%s_true" % (name, tag)] = _np(yy.grad)
+    xx, yy = aw[:, 2:].clone().requires_grad_(True), bw[:, 2:].clone().requires_grad_(True)
+    ns.loss.IOULoss("mean")(xx, yy, mode="wh").backward()
+    out["g_iou_wh_mean_pre"], out["g_iou_wh_mean_true"] = _np(xx.grad), _np(yy.grad)
+    # BCE
+    logits = torch.randn(33, 7, generator=g) * 3
+    idx = torch.randint(0, 7, (33,), generator=g)
+    out["bce_logits"], out["bce_idx"] = _np(logits), _np(idx)
+    for red in ("mean", "sum"):
+        x = logits.clone().requires_grad_(True)
+        ns.loss.BiCrossEntropyLoss(red)(x, idx).backward()
+        out["g_bce_%s" % red] = _np(x.grad)
+    x = logits.sigmoid().clone().requires_grad_(True)
+    ns.loss.BiCrossEntropyLoss("mean")(x, idx, already_sigmoid=True).backward()
+    out["g_bce_sig_mean"] = _np(x.grad)
+    one = torch.randn(50, 1, generator=g) * 3
+    tgt = torch.rand(50, 1, generator=g)
+    out["bce1_logits"], out["bce1_tgt"] = _np(one), _np(tgt)
+    x = one.clone().requires_grad_(True)
+    ns.loss.BiCrossEntropyLoss("mean")(x, tgt).backward()
+    out["g_bce1_mean"] = _np(x.grad)
+    np.savez_compressed(os.path.join(OUT, "grads_small.npz"), **out)
+
+
 def main():
     if "--only-frcnn-nms" in sys.argv:
         torch.set_num_threads(1)
         gold_frcnn_nms(ref_shim.load())
+        return
+    if "--only-grads" in sys.argv:
+        torch.set_num_threads(1)
+        gold_grads(ref_shim.load())
         return
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -291,6 +367,7 @@ def main():
     gold_map(ns)
     gold_rpn(ns)
     gold_frcnn_nms(ns)
+    gold_grads(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -47,3 +47,8 @@ def golden_rpn():
 
 def T(x):
     return torch.from_numpy(np.ascontiguousarray(x))
+
+
+@pytest.fixture(scope="session")
+def golden_grads():
+    return load_golden("grads_small.npz")

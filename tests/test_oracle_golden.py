@@ -200,3 +200,46 @@ def test_nms_frcnn_flavour_vs_reference_golden():
         thr, iou, md = g[tag + "_cfg"]
         out = on.nms_frcnn(T(g[tag + "_pred"]), float(thr), float(iou), int(md))
         assert np.array_equal(out.numpy(), g[tag + "_out"]), tag
+
+
+def GCLOSE(a, b):
+    """Gradients: rtol 1e-5 with an absolute floor of 1e-6 of the largest entry (sums of signed terms cancel)."""
+    CLOSE(a, b, rtol=1e-5, atol=1e-6 * float(np.abs(b).max()))
+
+
+# ---- gradients: autograd through the oracle vs gradients recorded from the reference's own graph ------------------------
+def test_yolov3_loss_grads(golden_grads):
+    g = golden_grads
+    heads = [T(g["head%d" % i]) for i in range(3)]
+    labels = T(g["labels"])
+    loss, grads = oracle.grad.yolov3_loss_grad(heads, labels, SMALL.anchors_levels(), SMALL.strides, upstream=float(g["upstream"]))
+    CLOSE(loss, g["loss"])
+    for i in range(3):
+        GCLOSE(grads[i], g["grad%d" % i])
+    _, grads0 = oracle.grad.yolov3_loss_grad(heads, labels[:0], SMALL.anchors_levels(), SMALL.strides)
+    for i in range(3):
+        GCLOSE(grads0[i], g["grad_nolabels%d" % i])
+
+
+@pytest.mark.parametrize("kind", ["iou", "giou", "diou", "ciou"])
+def test_iou_loss_grads(golden_grads, kind):
+    g = golden_grads
+    cases = {"xyxy_mean": ("a", "b", "xyxy", "mean", None), "xywh_sum": ("a_xywh", "b_xywh", "xywh", "sum", None),
+             "xyxy_mean_w": ("a", "b", "xyxy", "mean", T(g["w"]))}
+    for tag, (x, y, mode, red, w) in cases.items():
+        _, ga, gb = oracle.grad.iou_loss_grad(kind, T(g[x]), T(g[y]), w, mode, red)
+        GCLOSE(ga, g["g_%s_%s_pre" % (kind, tag)])
+        GCLOSE(gb, g["g_%s_%s_true" % (kind, tag)])
+    if kind == "iou":
+        _, ga, gb = oracle.grad.iou_loss_grad("iou", T(g["a_xywh"])[:, 2:], T(g["b_xywh"])[:, 2:], None, "wh", "mean")
+        GCLOSE(ga, g["g_iou_wh_mean_pre"])
+        GCLOSE(gb, g["g_iou_wh_mean_true"])
+
+
+def test_bce_loss_grads(golden_grads):
+    g = golden_grads
+    logits, idx = T(g["bce_logits"]), T(g["bce_idx"])
+    for red in ("mean", "sum"):
+        GCLOSE(oracle.grad.bce_loss_grad(logits, idx, reduction=red)[1], g["g_bce_%s" % red])
+    GCLOSE(oracle.grad.bce_loss_grad(logits.sigmoid(), idx, already_sigmoid=True)[1], g["g_bce_sig_mean"])
+    GCLOSE(oracle.grad.bce_loss_grad(T(g["bce1_logits"]), T(g["bce1_tgt"]))[1], g["g_bce1_mean"])
