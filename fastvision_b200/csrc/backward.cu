@@ -5,7 +5,9 @@
 //
 //   yolo_grad_dense  : HBM-bound stream.  Writes the whole gradient of every level tensor [B,A,H,W,K]: zero
 //                      everywhere except channel 4, which gets the objectness-BCE gradient for target 0 (the dense term
-//                      of yolov3_loss.py:63-64).  One 16-byte store per 4 floats, one 4-byte load per K floats.
+//                      of yolov3_loss.py:63-64).  One 16-byte store per 4 floats; the objectness logits come from the compact
+//                      copy the forward saved (4 bytes per row) -- read strided from the heads they cost a 128-byte DRAM
+//                      fetch per row (ncu: 349 MB of reads next to 869 MB of writes at B=256).
 //   yolo_grad_match  : one warp per (level, target, anchor).  The LAST match of a cell (the one whose IoU the reference's
 //                      index_put keeps, :61) owns the cell's row: it adds, in target order, the class-BCE, CIoU and
 //                      IoU-target gradients of every match that hit the cell (autograd's index backward scatter-adds
@@ -26,6 +28,8 @@ struct GradParams {
   const float* labels;
   int T;
   const int* flags;        // [0] labels grouped by image
+  const float* saved_conf; // compact objectness logits from the forward ([l][b][row]) or NULL (strided loads from the heads)
+  long long saved_off[FVB_MAX_LEVELS];
   float r_box, r_conf, r_cls;
   long long batch_global;
   // dense pass
@@ -50,8 +54,15 @@ __device__ __forceinline__ float dense_conf_grad(float logit, float coef) {
   return coef * (bce_dp(pr, 0.0f) * ((1.0f - pr) * pr));  // sigmoid backward: grad * (1 - y) * y
 }
 
+// Two phases per CTA (one 64 KB chunk of one level tensor): (1) the chunk's <= kDenseChunk/K + 1 objectness logits are
+// loaded with one thread per row -- every strided load of the CTA is in flight at once (a load is a 32-byte sector per
+// K*4-byte row; issued lazily from the store loop they were latency-bound: 41 % of the HBM peak) -- turned into gradients
+// and parked in shared memory; (2) the chunk is written with 16-byte stores, channel-4 slots picked from shared memory.
+constexpr int kDenseMaxRows = kDenseChunk / 6 + 2;  // K >= 6
+
 template <bool VEC>
 __global__ void __launch_bounds__(kDenseThreads) yolo_grad_dense_kernel(const GradParams p) {
+  __shared__ float s_grad[kDenseMaxRows];
   int l = 0;
 #pragma unroll
   for (int i = 1; i < FVB_MAX_LEVELS; ++i)
@@ -59,42 +70,68 @@ __global__ void __launch_bounds__(kDenseThreads) yolo_grad_dense_kernel(const Gr
   const int K = p.g.K;
   const long long n = p.lvl_floats[l];
   const long long base = (long long)((int)blockIdx.x - p.cta_begin[l]) * kDenseChunk;
+  const long long stop = min(base + (long long)kDenseChunk, n);
   const float* __restrict__ head = p.g.head[l];
   float* __restrict__ out = p.grad[l];
   const float coef = conf_coef(p, l, upstream(p));
+  // rows whose channel-4 element (float index r*K + 4) lies in [base, stop)
+  const long long first_row = base <= 4 ? 0 : (base - 4 + K - 1) / K;
+  const int n_rows = (int)max(0ll, (stop - 4 + K - 1) / K - first_row);
+  if (p.saved_conf != nullptr) {
+    const float* __restrict__ sc = p.saved_conf + p.saved_off[l] + first_row;  // coalesced: 4 bytes per row instead of a sector
+    for (int r = threadIdx.x; r < n_rows; r += kDenseThreads) s_grad[r] = dense_conf_grad(__ldg(sc + r), coef);
+  } else {
+    for (int r = threadIdx.x; r < n_rows; r += kDenseThreads)
+      s_grad[r] = dense_conf_grad(__ldg(head + (first_row + r) * K + 4), coef);
+  }
+  __syncthreads();
   if (VEC) {
-    // thread's first float index and its channel; consecutive iterations advance by 4*kDenseThreads floats
+    // thread's first float index, its row and channel; consecutive iterations advance by 4*kDenseThreads floats
     long long i = base + (long long)threadIdx.x * 4;
-    int c = (int)(i % K);
-    const int step_c = (4 * kDenseThreads) % K;
+    const long long row0 = i / K;
+    int c = (int)(i - row0 * K);
+    int rl = (int)(row0 - first_row);  // row of float i, relative to the first staged row (may be -1)
+    const int step_c = (4 * kDenseThreads) % K, step_r = (4 * kDenseThreads) / K;
 #pragma unroll 4
     for (int it = 0; it < kDenseIters; ++it) {
       if (i + 3 < n) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        // which of the four floats (if any) is channel 4:  e = (4 - c) mod K
-        int e = 4 - c;
-        if (e < 0) e += K;
+        // which of the four floats (if any) is channel 4: e = (4 - c) mod K; K >= 6 > 4: at most one per float4
+        int e = 4 - c, rr = rl;
+        if (e < 0) {
+          e += K;
+          rr += 1;
+        }
         if (e < 4) {
-          const float gq = dense_conf_grad(__ldg(head + i + e), coef);
+          const float gq = s_grad[rr];
           if (e == 0) v.x = gq; else if (e == 1) v.y = gq; else if (e == 2) v.z = gq; else v.w = gq;
         }
-        // K >= 6 > 4: at most one channel-4 element per float4
         __stcs(reinterpret_cast<float4*>(out + i), v);
       } else {
         for (int e = 0; e < 4 && i + e < n; ++e) {
-          int ce = c + e;
-          if (ce >= K) ce -= K;
-          out[i + e] = ce == 4 ? dense_conf_grad(__ldg(head + i + e), coef) : 0.0f;
+          int ce = c + e, rr = rl;
+          if (ce >= K) {
+            ce -= K;
+            rr += 1;
+          }
+          out[i + e] = ce == 4 ? s_grad[rr] : 0.0f;
         }
       }
       i += 4 * kDenseThreads;
       c += step_c;
-      if (c >= K) c -= K;
+      rl += step_r;
+      if (c >= K) {
+        c -= K;
+        rl += 1;
+      }
     }
   } else {
     for (int it = 0; it < kDenseIters * 4; ++it) {
       const long long i = base + (long long)it * kDenseThreads + threadIdx.x;
-      if (i < n) out[i] = (int)(i % K) == 4 ? dense_conf_grad(__ldg(head + i), coef) : 0.0f;
+      if (i < n) {
+        const long long row = i / K;
+        out[i] = (int)(i - row * K) == 4 ? s_grad[(int)(row - first_row)] : 0.0f;
+      }
     }
   }
 }
@@ -306,8 +343,8 @@ extern "C" size_t fvb_yolov3_loss_backward_workspace_bytes(void) { return 256; }
 
 extern "C" int fvb_yolov3_loss_backward_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
                                             int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
-                                            int64_t batch_global, const double* d_partials, const float* d_grad_out,
-                                            float* const* d_grad_heads, void* d_ws, void* stream) {
+                                            int64_t batch_global, const double* d_partials, const float* d_saved_conf,
+                                            const float* d_grad_out, float* const* d_grad_heads, void* d_ws, void* stream) {
   FVB_REQUIRE(d_heads && d_grad_heads && d_partials && d_ws, "yolov3_loss_backward: NULL pointer");
   FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "yolov3_loss_backward: num_labels=%lld", (long long)num_labels);
   FVB_REQUIRE(num_labels == 0 || d_labels, "yolov3_loss_backward: labels NULL");
@@ -329,12 +366,14 @@ extern "C" int fvb_yolov3_loss_backward_f32(const fvb_yolo_geom* geom, const flo
     p.grad[l] = d_grad_heads[l];
     p.lvl_floats[l] = (long long)g.B * g.A * g.HW[l] * g.K;
     p.cta_begin[l] = (int)ctas;
+    p.saved_off[l] = (long long)g.B * g.row_off[l];
     ctas += (p.lvl_floats[l] + kDenseChunk - 1) / kDenseChunk;
     if (((uintptr_t)d_grad_heads[l] & 15) != 0) vec = false;
   }
   for (int l = g.L; l <= FVB_MAX_LEVELS; ++l) p.cta_begin[l] = (int)ctas;
   FVB_REQUIRE(ctas < (1ll << 31), "yolov3_loss_backward: tensor too large for one launch");
   p.grad_out = d_grad_out;
+  p.saved_conf = d_saved_conf;
   p.partials = d_partials;
   p.labels = d_labels;
   p.T = (int)num_labels;

@@ -149,6 +149,8 @@ struct StreamParams {
   int chunk_off[FVB_MAX_LEVELS + 1];  // first partial of each level
   int chunks[FVB_MAX_LEVELS];         // chunks per image on each level
   double* partials;
+  float* save;                        // optional compact copy of the objectness logits, level-major [l][b][row] (for the backward)
+  long long save_off[FVB_MAX_LEVELS];
 };
 
 __global__ void __launch_bounds__(256) conf_stream_kernel(const StreamParams p) {
@@ -167,7 +169,11 @@ __global__ void __launch_bounds__(256) conf_stream_kernel(const StreamParams p) 
   for (int i = 0; i < kStreamRows / 256; ++i) {
     int r = r0 + i * 256 + threadIdx.x;
     // same arithmetic as the fused partials of the decode kernel: objectness as decode stores it, target 0
-    if (r < rows) acc += (double)bce_term_zero(sigmoid_fast(__ldg(base + (size_t)r * p.g.K)));
+    if (r < rows) {
+      const float logit = __ldg(base + (size_t)r * p.g.K);
+      acc += (double)bce_term_zero(sigmoid_fast(logit));
+      if (p.save != nullptr) p.save[p.save_off[l] + (long long)b * rows + r] = logit;
+    }
   }
   __shared__ double scratch[32];
   double s = block_sum(acc, scratch);
@@ -361,6 +367,20 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
                                    int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
                                    const double* d_conf_bce0, double* d_partials, float* d_out_loss, void* d_ws,
                                    void* stream) {
+  return fvb_yolov3_loss_train_f32(geom, d_heads, d_labels, num_labels, ratio_box, ratio_conf, ratio_cls, d_conf_bce0,
+                                   d_partials, d_out_loss, nullptr, d_ws, stream);
+}
+
+extern "C" int64_t fvb_yolov3_saved_conf_floats(const fvb_yolo_geom* geom) {
+  Geom g;
+  if (make_geom(geom, nullptr, &g) != FVB_OK) return 0;
+  return (int64_t)g.B * g.row_off[g.L];
+}
+
+extern "C" int fvb_yolov3_loss_train_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                         int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                                         const double* d_conf_bce0, double* d_partials, float* d_out_loss,
+                                         float* d_saved_conf, void* d_ws, void* stream) {
   FVB_REQUIRE(d_heads && d_partials && d_ws, "yolov3_loss: NULL pointer");
   FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "yolov3_loss: num_labels=%lld", (long long)num_labels);
   FVB_REQUIRE(num_labels == 0 || d_labels, "yolov3_loss: labels NULL");
@@ -390,7 +410,7 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
   fp.r_conf = ratio_conf;
   fp.r_cls = ratio_cls;
   fp.batch_global = g.B;
-  if (d_conf_bce0) {
+  if (d_conf_bce0 && d_saved_conf == nullptr) {
     fp.conf0 = d_conf_bce0;
     const int tr = decode_tile_rows(g.K);  // the decode kernel wrote one partial per tile, level-major
     int t = 0;
@@ -406,12 +426,14 @@ extern "C" int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const
     for (int l = 0; l < g.L; ++l) {
       sp.chunk_off[l] = t;
       sp.chunks[l] = stream_chunks(g, l);
+      sp.save_off[l] = (long long)g.B * g.row_off[l];
       fp.level_begin[l] = t;
       t += sp.chunks[l] * g.B;
       fp.level_end[l] = t;
     }
     for (int l = g.L; l <= FVB_MAX_LEVELS; ++l) sp.chunk_off[l] = t;
     sp.partials = stream_parts;
+    sp.save = d_saved_conf;
     conf_stream_kernel<<<t, 256, 0, s>>>(sp);
     count_launch();
     fp.conf0 = stream_parts;

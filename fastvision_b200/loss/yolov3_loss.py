@@ -21,8 +21,9 @@ class _Yolov3LossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(fctx, module, labels, geom_ctx, conf_bce0, out, partials, batch_global, *heads):
-        loss = module._forward_impl(list(heads), labels, geom_ctx, conf_bce0, out, partials)
-        fctx.module, fctx.geom_ctx, fctx.labels = module, geom_ctx, labels
+        saved = torch.empty(int(_lib.load().fvb_yolov3_saved_conf_floats(geom_ctx.geom)), dtype=torch.float32, device=geom_ctx.device)
+        loss = module._forward_impl(list(heads), labels, geom_ctx, conf_bce0, out, partials, saved_conf=saved)
+        fctx.module, fctx.geom_ctx, fctx.labels, fctx.saved_conf = module, geom_ctx, labels, saved
         fctx.partials, fctx.batch_global = module.partials, batch_global
         fctx.save_for_backward(*heads)
         return loss
@@ -30,7 +31,8 @@ class _Yolov3LossFn(torch.autograd.Function):
     @staticmethod
     def backward(fctx, grad_out):
         heads = fctx.saved_tensors
-        grads = fctx.module.backward_heads(list(heads), fctx.labels, grad_out, fctx.partials, fctx.batch_global, ctx=fctx.geom_ctx)
+        grads = fctx.module.backward_heads(list(heads), fctx.labels, grad_out, fctx.partials, fctx.batch_global, ctx=fctx.geom_ctx,
+                                           saved_conf=fctx.saved_conf)
         return (None, None, None, None, None, None, None) + tuple(grads)
 
 
@@ -70,7 +72,7 @@ class Yolov3Loss(nn.Module):
             return _Yolov3LossFn.apply(self, labels.detach(), ctx, conf_bce0, out, partials, None, *heads)
         return self._forward_impl(heads, labels, ctx, conf_bce0, out, partials)
 
-    def _forward_impl(self, heads, labels, ctx, conf_bce0, out, partials):
+    def _forward_impl(self, heads, labels, ctx, conf_bce0, out, partials, saved_conf=None):
         dev = ctx.device
         t = labels.size(0)
         if out is None:
@@ -80,18 +82,20 @@ class Yolov3Loss(nn.Module):
         lib = _lib.load()
         ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, t), dev, "yolov3_loss")
         with torch.cuda.device(dev):
-            _lib.check(lib.fvb_yolov3_loss_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
-                                               float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
-                                               _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
-                                               _lib.dptr(ws), _lib.stream()), "yolov3_loss")
+            _lib.check(lib.fvb_yolov3_loss_train_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
+                                                     float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
+                                                     _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
+                                                     _lib.dptr(saved_conf), _lib.dptr(ws), _lib.stream()), "yolov3_loss")
         self.partials = partials
         return out
 
-    def backward_heads(self, y_pred, y_true, grad_out=None, partials=None, batch_global=None, ctx=None, grads=None):
+    def backward_heads(self, y_pred, y_true, grad_out=None, partials=None, batch_global=None, ctx=None, grads=None,
+                       saved_conf=None):
         """Gradients of ``forward`` w.r.t. the raw head tensors (list of [B,A,H,W,K], written completely).
 
         ``partials``: the forward's [L,4] partials (all-reduced under data parallelism, together with ``batch_global``);
-        ``grad_out``: the upstream gradient (Tensor[1] on the device) or None for 1.
+        ``grad_out``: the upstream gradient (Tensor[1] on the device) or None for 1;
+        ``saved_conf``: the compact objectness logits the training forward wrote (None: strided re-read of the heads).
         """
         heads = [_lib.require_cuda(h.detach(), "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
         labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
@@ -110,7 +114,8 @@ class Yolov3Loss(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(lib.fvb_yolov3_loss_backward_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), labels.size(0),
                                                         float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
-                                                        bg, _lib.dptr(partials), _lib.dptr(grad_out), _lib.head_ptrs(grads),
+                                                        bg, _lib.dptr(partials), _lib.dptr(saved_conf), _lib.dptr(grad_out),
+                                                        _lib.head_ptrs(grads),
                                                         _lib.dptr(ws), _lib.stream()), "yolov3_loss_backward")
         return grads
 

@@ -194,6 +194,14 @@ int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const* d_heads, 
                         int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
                         const double* d_conf_bce0, double* d_partials, float* d_out_loss, void* d_ws,
                         void* stream);
+/* Training form of the same call: additionally writes d_saved_conf ([fvb_yolov3_saved_conf_floats(geom)] f32, may be
+ * NULL), a compact level-major copy [l][b][row] of the objectness logits, which fvb_yolov3_loss_backward_f32 then reads
+ * instead of striding through the heads again.  With d_saved_conf the call always streams channel 4 itself. */
+int64_t fvb_yolov3_saved_conf_floats(const fvb_yolo_geom* geom);
+int fvb_yolov3_loss_train_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                              int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                              const double* d_conf_bce0, double* d_partials, float* d_out_loss, float* d_saved_conf,
+                              void* d_ws, void* stream);
 /* Combine (all-reduced) partials into the scalar; batch_global/cells use the GLOBAL batch. */
 int fvb_yolov3_loss_combine_f32(const fvb_yolo_geom* geom, int64_t batch_global, const double* d_partials,
                                 float ratio_box, float ratio_conf, float ratio_cls, float* d_out_loss,
@@ -213,14 +221,15 @@ int fvb_yolov3_build_target_f32(const fvb_yolo_geom* geom, int level, const floa
  * (:50-52), CIoU (:54-58, alpha constant as in detection/tools/IOU.py:436-437) and IoU-target (:60-61, the reference
  * does not detach targets_conf) gradients; duplicate matches of one cell accumulate as torch's index / index_put
  * backward do.  d_partials: the [L*4] f64 partials of the forward (M_l at [l*4+3]; all-reduced under data
- * parallelism, with batch_global the global batch).  d_grad_out: device scalar [1] (the upstream gradient) or NULL
+ * parallelism, with batch_global the global batch).  d_saved_conf: the compact objectness logits written by
+ * fvb_yolov3_loss_train_f32 over the same heads, or NULL.  d_grad_out: device scalar [1] (the upstream gradient) or NULL
  * for 1.  d_ws: fvb_yolov3_loss_backward_workspace_bytes() bytes.  Bit-reproducible (one writer per row, no atomics).
  */
 size_t fvb_yolov3_loss_backward_workspace_bytes(void);
 int fvb_yolov3_loss_backward_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
                                  int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
-                                 int64_t batch_global, const double* d_partials, const float* d_grad_out,
-                                 float* const* d_grad_heads, void* d_ws, void* stream);
+                                 int64_t batch_global, const double* d_partials, const float* d_saved_conf,
+                                 const float* d_grad_out, float* const* d_grad_heads, void* d_ws, void* stream);
 /* Gradients of fvb_iou_loss_f32 (loss/iou_loss.py:5-107) w.r.t. y_pre and/or y_true (either output may be NULL);
  * same box_mode layout as the inputs ([n,4], or [n,2] for wh).  torch conventions: minimum/maximum split ties 1/2,
  * clamp(0) passes the gradient at 0.  d_ws: >= 256 bytes. */

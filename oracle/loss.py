@@ -112,7 +112,7 @@ def yolov3_loss(y_pred, y_true, anchors_per_level, strides, ratio_box=0.05, rati
             loss_cls += l_cls
             loss_box += l_box
         loss_conf += l_conf
-        partials.append([float(sums[0]), float(sums[1]), float(sums[2]), float(sums[3])])
+        partials.append([float(torch.as_tensor(v).detach()) for v in sums])
     loss_box *= ratio_box
     loss_conf *= ratio_conf
     loss_cls *= ratio_cls
