@@ -18,6 +18,7 @@ DECODE_FORMS = {"v3": 0, "v5": 1}
 HEAD_LAYOUTS = {"bahwk": 0, "nchw": 1}
 NMS_FLAVOURS = {"lib": 0, "demo": 1, "demo_batch": 2}
 REDUCTIONS = {"mean": 0, "sum": 1}
+DEMO_LOSS_FLAVOURS = {"ship": 0, "u": 1}
 
 
 class Geom(C.Structure):
@@ -70,6 +71,12 @@ _SIGS = {
     "fvb_iou_loss_backward_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P, _P,
                                             _P, _P]),
     "fvb_bce_loss_backward_f32": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "fvb_demo_loss_workspace_bytes": (C.c_size_t, [C.POINTER(Geom), C.c_int64]),
+    "fvb_demo_loss_mask_bytes": (C.c_int64, [C.POINTER(Geom)]),
+    "fvb_demo_loss_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P]),
+    "fvb_demo_loss_combine_f32": (C.c_int, [C.POINTER(Geom), _P, C.c_int, _P, _P]),
+    "fvb_demo_loss_backward_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_int, _P, _P, _P,
+                                             C.POINTER(_P), _P, _P]),
     "fvb_map_match_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "fvb_map_match_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int, _P, _P, _P]),
 }

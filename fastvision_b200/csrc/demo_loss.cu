@@ -1,0 +1,664 @@
+// The demos' training loss `ComputeLoss`, forward and backward, on the raw conv outputs [B, A*K, H, W]:
+//   flavour SHIP  demos/yolov3_huaweiShip/utils/lossv3.py:19-125  -> (loss_box [CIoU, demo variant], loss_cls, loss_conf)
+//   flavour U     demos/yolov3_u/utils/lossv3.py:17-119           -> 2*loss_xy + loss_wh + loss_cls + loss_conf
+// Per level every target is assigned to its best anchor by wh-IoU (first maximum) and to the cell floor(xy); the
+// objectness target is 1 at those cells, "ignore" where the predicted box of a cell overlaps any target of its image by
+// IoU > 0.5 (the reference's per-image Python loop over xywh_iou_batch([A*H*W,4],[T_i,4]), lossv3.py:102-113) and 0
+// elsewhere; every term is a mean (BCE-with-logits / MSE / 1-CIoU).
+//
+//   demo_prep     : keys (cell ids) of every (level, target) + per-image target lists (counting sort, one CTA)
+//   demo_targets  : one warp per (level, target): gather the matched row from the NCHW planes, box / xy-wh and class terms
+//   demo_cells    : HBM-bound stream over the 5 head planes of every anchor: decode the box, max pairwise IoU against the
+//                   image's targets staged in shared memory, ignore / positive / negative, objectness BCE; optionally
+//                   saves the int8 mask for the backward.  Reads 5 of K planes: 20 bytes per predicted box.
+//   demo_finalize : fixed-order fp64 reduction -> per-level partials {S_a, S_b, S_cls, S_conf, n_valid, T} + the outputs
+//   demo_grad_dense / demo_grad_targets : backward (whole gradient written, single writer per row, no atomics)
+#include "iou_grad.cuh"
+
+namespace fvb {
+
+constexpr int kDemoParts = 6;  // per level: S_a (box | xy), S_b (wh, flavour U), S_cls, S_conf, n_valid, T
+constexpr int kCellThreads = 256;
+constexpr int kCellBoxes = 4;  // boxes per thread
+constexpr int kCellChunk = kCellThreads * kCellBoxes;
+constexpr int kStage = 64;     // targets staged per round
+constexpr int kTgtThreads = 256;
+
+// F.binary_cross_entropy_with_logits element: (1 - t) * x - log_sigmoid(x), log_sigmoid(x) = min(x,0) - log1p(exp(-|x|))
+FVB_HD float bce_logits(float x, float t) { return (1.0f - t) * x - (fminf(x, 0.0f) - log1pf(expf(-fabsf(x)))); }
+
+struct DemoTarget {
+  bool ok;
+  int b, cls, gx, gy, a;
+  float x, y, w, h;  // feature units
+  float offx, offy, aw, ah;
+};
+
+// lossv3.py:46-62: scale to the feature map, best anchor by wh_iou_batch (first maximum), cell = floor(xy)
+FVB_HD DemoTarget demo_target(const Geom& g, int l, const float* lab) {
+  DemoTarget t;
+  const float fw = (float)g.W[l], fh = (float)g.H[l];
+  t.b = (int)lab[0];
+  t.cls = (int)lab[1];
+  t.x = lab[2] * fw;
+  t.y = lab[3] * fh;
+  t.w = lab[4] * fw;
+  t.h = lab[5] * fh;
+  float best = -1.0f;
+  t.a = 0;
+  t.aw = t.ah = 1.0f;
+  for (int a = 0; a < g.A; ++a) {
+    const float aw = g.aw[l][a] / g.stride[l], ah = g.ah[l][a] / g.stride[l];
+    const float v = wh_iou(t.w, t.h, aw, ah, 1e-7f);
+    if (a == 0 || v > best) {  // torch.max(dim=1): first maximum
+      best = v;
+      t.a = a;
+      t.aw = aw;
+      t.ah = ah;
+    }
+  }
+  const float fx = floorf(t.x), fy = floorf(t.y);
+  t.offx = t.x - fx;
+  t.offy = t.y - fy;
+  // the reference indexes with the raw floor (IndexError / negative wrap when a centre leaves the map); clamped here
+  t.gx = (int)fminf(fmaxf(fx, 0.0f), (float)(g.W[l] - 1));
+  t.gy = (int)fminf(fmaxf(fy, 0.0f), (float)(g.H[l] - 1));
+  t.ok = t.b >= 0 && t.b < g.B && t.cls >= 0 && t.cls < g.K - 5;
+  return t;
+}
+
+struct DemoParams {
+  Geom g;
+  const float* labels;
+  int T, flavour;
+  // workspace
+  int* key;        // [L][T]  (b*A + a)*HW + cell, or -1
+  int* img_off;    // [B+1]
+  int* img_cur;    // [B]
+  int* img_list;   // [T] target ids grouped by image
+  double* tgt_ws;  // [L][tgt_blocks][4]
+  double* cell_ws; // [cell_ctas][2]
+  int tgt_blocks;
+  int cell_cta_begin[FVB_MAX_LEVELS + 1];
+  int cell_chunks[FVB_MAX_LEVELS];   // CTAs per image on each level
+  long long mask_off[FVB_MAX_LEVELS];
+  signed char* mask;  // optional [l][b][a][cell]
+  double* partials;   // [L][kDemoParts]
+  float* out;         // [3]
+};
+
+__global__ void __launch_bounds__(1024) demo_prep_kernel(const DemoParams p) {
+  const int B = p.g.B, T = p.T;
+  for (int i = threadIdx.x; i <= B; i += blockDim.x) p.img_off[i] = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) p.img_cur[i] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float* lab = p.labels + (size_t)t * 6;
+    const int b = (int)lab[0];
+    if (b >= 0 && b < B) atomicAdd(&p.img_off[b + 1], 1);
+    for (int l = 0; l < p.g.L; ++l) {
+      const DemoTarget d = demo_target(p.g, l, lab);
+      p.key[(size_t)l * T + t] = d.ok ? (d.b * p.g.A + d.a) * p.g.HW[l] + d.gy * p.g.W[l] + d.gx : -1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {  // inclusive scan of the counts, 32 at a time
+    int carry = 0;
+    for (int base = 1; base <= B; base += 32) {
+      const int i = base + threadIdx.x;
+      int v = i <= B ? p.img_off[i] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)threadIdx.x >= o) v += u;
+      }
+      if (i <= B) p.img_off[i] = v + carry;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int b = (int)p.labels[(size_t)t * 6];
+    if (b >= 0 && b < B) p.img_list[p.img_off[b] + atomicAdd(&p.img_cur[b], 1)] = t;
+  }
+}
+
+// address of channel k of the matched row in the NCHW tensor
+__device__ __forceinline__ size_t nchw_at(const Geom& g, int l, int b, int a, int k, int cell) {
+  return ((size_t)(b * g.A + a) * g.K + k) * g.HW[l] + cell;
+}
+
+__global__ void __launch_bounds__(kTgtThreads) demo_targets_kernel(const DemoParams p) {
+  __shared__ double part[kTgtThreads / 32][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = blockIdx.y;
+  const int t = blockIdx.x * (kTgtThreads / 32) + warp;
+  double s_a = 0.0, s_b = 0.0, s_cls = 0.0, cnt = 0.0;
+  if (t < p.T) {
+    const DemoTarget d = demo_target(p.g, l, p.labels + (size_t)t * 6);
+    if (d.ok) {
+      const int K = p.g.K, cell = d.gy * p.g.W[l] + d.gx;
+      const float* head = p.g.head[l];
+      const float first = lane < K ? head[nchw_at(p.g, l, d.b, d.a, lane, cell)] : 0.0f;
+      double sc = 0.0;
+      for (int ch = lane; ch < K; ch += 32) {
+        if (ch < 5) continue;
+        const float v = ch < 32 ? first : head[nchw_at(p.g, l, d.b, d.a, ch, cell)];
+        sc += (double)bce_logits(v, (ch - 5 == d.cls) ? 1.0f : 0.0f);   // lossv3.py:92-95
+      }
+      s_cls = warp_sum(sc);
+      const float r0 = __shfl_sync(0xffffffffu, first, 0), r1 = __shfl_sync(0xffffffffu, first, 1);
+      const float r2 = __shfl_sync(0xffffffffu, first, 2), r3 = __shfl_sync(0xffffffffu, first, 3);
+      if (p.flavour == FVB_DEMO_LOSS_SHIP) {
+        // predict_xywh = [sigmoid + grid, exp * anchor] (lossv3.py:65-69) vs the target in feature units (:85-88)
+        const float px = sigmoid_precise(r0) + (float)d.gx, py = sigmoid_precise(r1) + (float)d.gy;
+        const float pw = expf(r2) * d.aw, ph = expf(r3) * d.ah;
+        const float ciou = iou_family<false>(xywh_to_xyxy(px, py, pw, ph), xywh_to_xyxy(d.x, d.y, d.w, d.h), FVB_CIOU,
+                                             FVB_VARIANT_DEMO, 1e-7f);
+        s_a = (double)(1.0f - ciou);
+      } else {
+        // yolov3_u/utils/lossv3.py:71-78: BCE-with-logits on the xy logits, MSE on the wh logits
+        s_a = (double)bce_logits(r0, d.offx) + (double)bce_logits(r1, d.offy);
+        const float tw = logf(d.w / d.aw + 1e-14f), th = logf(d.h / d.ah + 1e-14f);
+        const float dw = r2 - tw, dh = r3 - th;
+        s_b = (double)(dw * dw) + (double)(dh * dh);
+      }
+      cnt = 1.0;
+    }
+  }
+  if (lane == 0) {
+    part[warp][0] = s_a;
+    part[warp][1] = s_b;
+    part[warp][2] = s_cls;
+    part[warp][3] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTgtThreads / 32; ++w) s += part[w][threadIdx.x];
+    p.tgt_ws[((size_t)l * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kCellThreads) demo_cells_kernel(const DemoParams p) {
+  __shared__ Box s_box[kStage];
+  __shared__ int s_key[kStage];
+  __shared__ double scratch[32];
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < FVB_MAX_LEVELS; ++i)
+    if (i < p.g.L && (int)blockIdx.x >= p.cell_cta_begin[i]) l = i;
+  const int id = (int)blockIdx.x - p.cell_cta_begin[l];
+  const int b = id / p.cell_chunks[l], chunk = id - b * p.cell_chunks[l];
+  const int HW = p.g.HW[l], W = p.g.W[l], K = p.g.K;
+  const int boxes = p.g.A * HW;
+  const float* __restrict__ head = p.g.head[l] + (size_t)b * p.g.A * K * HW;
+
+  // this thread's boxes: decode (lossv3.py:65-69) and keep xyxy + objectness logit
+  Box pb[kCellBoxes];
+  float conf[kCellBoxes];
+  float best[kCellBoxes];
+  bool pos[kCellBoxes];
+#pragma unroll
+  for (int q = 0; q < kCellBoxes; ++q) {
+    const int j = chunk * kCellChunk + q * kCellThreads + threadIdx.x;
+    best[q] = -1.0f;
+    pos[q] = false;
+    conf[q] = 0.0f;
+    pb[q].x1 = pb[q].y1 = pb[q].x2 = pb[q].y2 = 0.0f;
+    if (j < boxes) {
+      const int a = j / HW, cell = j - a * HW;
+      const int gy = cell / W, gx = cell - gy * W;
+      const float* q0 = head + (size_t)a * K * HW + cell;
+      const float t0 = __ldg(q0), t1 = __ldg(q0 + HW), t2 = __ldg(q0 + 2 * (size_t)HW), t3 = __ldg(q0 + 3 * (size_t)HW);
+      conf[q] = __ldg(q0 + 4 * (size_t)HW);
+      const float aw = p.g.aw[l][a] / p.g.stride[l], ah = p.g.ah[l][a] / p.g.stride[l];
+      pb[q] = xywh_to_xyxy(sigmoid_precise(t0) + (float)gx, sigmoid_precise(t1) + (float)gy, expf(t2) * aw, expf(t3) * ah);
+    }
+  }
+  // targets of image b, kStage at a time
+  const int beg = p.img_off[b], end = p.img_off[b + 1];
+  const int key_base = b * p.g.A * HW;
+  for (int s0 = beg; s0 < end; s0 += kStage) {
+    const int ns = min(kStage, end - s0);
+    __syncthreads();
+    if ((int)threadIdx.x < ns) {
+      const int t = p.img_list[s0 + threadIdx.x];
+      const DemoTarget d = demo_target(p.g, l, p.labels + (size_t)t * 6);
+      s_box[threadIdx.x] = xywh_to_xyxy(d.x, d.y, d.w, d.h);
+      const int key = p.key[(size_t)l * p.T + t];
+      s_key[threadIdx.x] = key >= 0 ? key - key_base : -1;
+    }
+    __syncthreads();
+    for (int i = 0; i < ns; ++i) {
+      const Box tb = s_box[i];
+      const int tk = s_key[i];
+#pragma unroll
+      for (int q = 0; q < kCellBoxes; ++q) {
+        const float v = iou_plain<false>(pb[q], tb, 1e-7f);  // xywh_iou_batch (lossv3.py:106)
+        best[q] = fmaxf(best[q], v);
+        pos[q] = pos[q] || (tk == chunk * kCellChunk + q * kCellThreads + (int)threadIdx.x);
+      }
+    }
+  }
+  double sum = 0.0, cnt = 0.0;
+#pragma unroll
+  for (int q = 0; q < kCellBoxes; ++q) {
+    const int j = chunk * kCellChunk + q * kCellThreads + threadIdx.x;
+    if (j < boxes) {
+      // mask: -1 ignore (max IoU > 0.5, lossv3.py:110), then positives overwrite with 1 (:115)
+      const signed char m = pos[q] ? 1 : (best[q] > 0.5f ? -1 : 0);
+      if (p.mask) p.mask[p.mask_off[l] + (long long)b * boxes + j] = m;
+      if (m >= 0) {
+        sum += (double)bce_logits(conf[q], (float)m);  // :118-120
+        cnt += 1.0;
+      }
+    }
+  }
+  sum = block_sum(sum, scratch);
+  cnt = block_sum(cnt, scratch);
+  if (threadIdx.x == 0) {
+    p.cell_ws[(size_t)blockIdx.x * 2] = sum;
+    p.cell_ws[(size_t)blockIdx.x * 2 + 1] = cnt;
+  }
+}
+
+__device__ __forceinline__ void demo_combine(const Geom& g, const double* parts, int flavour, float* out) {
+  double a = 0.0, b2 = 0.0, c = 0.0, d = 0.0;
+  const int C = g.K - 5;
+  for (int l = 0; l < g.L; ++l) {
+    const double* q = parts + l * kDemoParts;
+    const double T = q[5];
+    if (flavour == FVB_DEMO_LOSS_SHIP) a += q[0] / T;  // (1 - ciou).mean()
+    else {
+      a += q[0] / (2.0 * T);                           // BCE-with-logits over [T,2]
+      b2 += q[1] / (2.0 * T);                          // MSE over [T,2]
+    }
+    c += q[2] / (T * C);
+    d += q[3] / q[4];
+  }
+  if (flavour == FVB_DEMO_LOSS_SHIP) {
+    out[0] = (float)a;
+    out[1] = (float)c;
+    out[2] = (float)d;
+  } else {
+    out[0] = (float)(2.0 * a + b2 + c + d);  // loss_xy *= 2.0; loss_xy + loss_wh + loss_cls + loss_conf
+    out[1] = 0.0f;
+    out[2] = 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(1024) demo_finalize_kernel(const DemoParams p) {
+  __shared__ double scratch[32];
+  for (int l = 0; l < p.g.L; ++l) {
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < p.tgt_blocks; i += blockDim.x)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] += p.tgt_ws[((size_t)l * p.tgt_blocks + i) * 4 + c];
+    double cs = 0.0, cn = 0.0;
+    for (int i = p.cell_cta_begin[l] + threadIdx.x; i < p.cell_cta_begin[l + 1]; i += blockDim.x) {
+      cs += p.cell_ws[(size_t)i * 2];
+      cn += p.cell_ws[(size_t)i * 2 + 1];
+    }
+    double r[6];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r[c] = block_sum(v[c], scratch);
+    r[4] = block_sum(cs, scratch);
+    r[5] = block_sum(cn, scratch);
+    if (threadIdx.x == 0) {
+      double* q = p.partials + l * kDemoParts;
+      q[0] = r[0]; q[1] = r[1]; q[2] = r[2]; q[3] = r[4]; q[4] = r[5]; q[5] = r[3];
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (threadIdx.x == 0 && p.out != nullptr) demo_combine(p.g, p.partials, p.flavour, p.out);
+}
+
+struct DemoCombineParams {
+  Geom g;
+  const double* partials;
+  int flavour;
+  float* out;
+};
+__global__ void demo_combine_kernel(const DemoCombineParams p) {
+  if (threadIdx.x == 0) demo_combine(p.g, p.partials, p.flavour, p.out);
+}
+
+// ---- backward ---------------------------------------------------------------------------------------------------------
+struct DemoGradParams {
+  Geom g;
+  const float* labels;
+  int T, flavour;
+  const int* key;             // [L][T] (demo_prep)
+  const signed char* mask;    // forward's mask
+  long long mask_off[FVB_MAX_LEVELS];
+  const double* partials;     // [L][kDemoParts] (all-reduced under data parallelism)
+  const float* grad_out;      // [3] (ship) / [1] (u), or NULL for ones
+  float* grad[FVB_MAX_LEVELS];
+  long long lvl_floats[FVB_MAX_LEVELS];
+  int cta_begin[FVB_MAX_LEVELS + 1];
+};
+
+constexpr int kDgThreads = 256;
+constexpr int kDgIters = 16;
+constexpr int kDgChunk = kDgThreads * kDgIters * 4;
+
+__device__ __forceinline__ float demo_up(const DemoGradParams& p, int which) {
+  if (!p.grad_out) return 1.0f;
+  return p.flavour == FVB_DEMO_LOSS_SHIP ? p.grad_out[which] : p.grad_out[0];
+}
+
+// whole gradient of one level tensor [B, A*K, H, W]: zero except the objectness planes, (sigmoid(x) - t) / n_valid there
+template <bool VEC>
+__global__ void __launch_bounds__(kDgThreads) demo_grad_dense_kernel(const DemoGradParams p) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < FVB_MAX_LEVELS; ++i)
+    if (i < p.g.L && (int)blockIdx.x >= p.cta_begin[i]) l = i;
+  const int HW = p.g.HW[l], K = p.g.K;
+  const long long n = p.lvl_floats[l];
+  const long long base = (long long)((int)blockIdx.x - p.cta_begin[l]) * kDgChunk;
+  const float* __restrict__ head = p.g.head[l];
+  float* __restrict__ out = p.grad[l];
+  const signed char* __restrict__ mask = p.mask + p.mask_off[l];
+  const float coef = (float)((double)demo_up(p, 2) / p.partials[l * kDemoParts + 4]);
+  auto elem = [&](long long i, int plane, int cell) -> float {
+    const int ba = plane / K;
+    if (plane - ba * K != 4) return 0.0f;
+    const signed char m = mask[(long long)ba * HW + cell];
+    if (m < 0) return 0.0f;
+    return coef * (sigmoid_precise(__ldg(head + i)) - (float)m);
+  };
+  const int step = VEC ? 4 * kDgThreads : kDgThreads;
+  long long i = base + (long long)threadIdx.x * (VEC ? 4 : 1);
+  int plane = (int)(i / HW);  // < B*A*K
+  int cell = (int)(i - (long long)plane * HW);
+  const int step_p = step / HW, step_c = step % HW;
+  for (int it = 0; it < (VEC ? kDgIters : kDgIters * 4); ++it) {
+    if (VEC) {
+      if (i + 3 < n) {
+        float4 v;
+        if (cell + 3 < HW) {
+          if (plane % K != 4) v = make_float4(0.f, 0.f, 0.f, 0.f);
+          else v = make_float4(elem(i, plane, cell), elem(i + 1, plane, cell + 1), elem(i + 2, plane, cell + 2), elem(i + 3, plane, cell + 3));
+        } else {
+          float e[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool wrap = cell + q >= HW;
+            e[q] = elem(i + q, wrap ? plane + 1 : plane, wrap ? cell + q - HW : cell + q);
+          }
+          v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        __stcs(reinterpret_cast<float4*>(out + i), v);
+      } else {
+        for (int q = 0; q < 4 && i + q < n; ++q) {
+          const bool wrap = cell + q >= HW;
+          out[i + q] = elem(i + q, wrap ? plane + 1 : plane, wrap ? cell + q - HW : cell + q);
+        }
+      }
+    } else if (i < n) {
+      out[i] = elem(i, plane, cell);
+    }
+    i += step;
+    plane += step_p;
+    cell += step_c;
+    if (cell >= HW) {
+      cell -= HW;
+      plane += 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTgtThreads) demo_grad_targets_kernel(const DemoGradParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = blockIdx.y;
+  const int t = blockIdx.x * (kTgtThreads / 32) + warp;
+  if (t >= p.T) return;
+  const int* keys = p.key + (size_t)l * p.T;
+  const int key = keys[t];
+  if (key < 0) return;
+  // the last target of a (cell, anchor) owns the row; earlier duplicates are added by it in target order
+  for (int b0 = t + 1; b0 < p.T; b0 += 32) {
+    const int t2 = b0 + lane;
+    if (__any_sync(0xffffffffu, t2 < p.T && keys[t2] == key)) return;
+  }
+  const DemoTarget self = demo_target(p.g, l, p.labels + (size_t)t * 6);
+  const int K = p.g.K, C = K - 5, HW = p.g.HW[l];
+  const int cell = self.gy * p.g.W[l] + self.gx;
+  const float* head = p.g.head[l];
+  float* grad = p.grad[l];
+  const double Tn = p.partials[l * kDemoParts + 5];
+  const float w_cls = (float)((double)demo_up(p, 1) / (Tn * C));
+  const float w_box = (float)((double)demo_up(p, 0) / Tn);
+  const float first = lane < K ? head[nchw_at(p.g, l, self.b, self.a, lane, cell)] : 0.0f;
+  const float r0 = __shfl_sync(0xffffffffu, first, 0), r1 = __shfl_sync(0xffffffffu, first, 1);
+  const float r2 = __shfl_sync(0xffffffffu, first, 2), r3 = __shfl_sync(0xffffffffu, first, 3);
+
+  auto add_target = [&](int t2) {
+    const DemoTarget d = t2 == t ? self : demo_target(p.g, l, p.labels + (size_t)t2 * 6);
+    float g4[4];
+    if (p.flavour == FVB_DEMO_LOSS_SHIP) {
+      const float sx = sigmoid_precise(r0), sy = sigmoid_precise(r1);
+      const float pw = expf(r2) * d.aw, ph = expf(r3) * d.ah;
+      BoxGrad ga = zero_grad(), gb = zero_grad();
+      iou_family_grad(xywh_to_xyxy(sx + (float)d.gx, sy + (float)d.gy, pw, ph), xywh_to_xyxy(d.x, d.y, d.w, d.h), FVB_CIOU,
+                      FVB_VARIANT_DEMO, 1e-7f, 0.0f - w_box, ga, gb);
+      float gx, gy, gw, gh;
+      xyxy_grad_to_xywh(ga, &gx, &gy, &gw, &gh);
+      g4[0] = gx * ((1.0f - sx) * sx);
+      g4[1] = gy * ((1.0f - sy) * sy);
+      g4[2] = gw * pw;
+      g4[3] = gh * ph;
+    } else {
+      // total = 2 * mean_{[T,2]} bce_logits(xy) + mean_{[T,2]} (wh - log(w/a))^2 + ...
+      const float w_xy = (float)((double)demo_up(p, 0) * 2.0 / (2.0 * Tn)), w_wh = (float)((double)demo_up(p, 0) / (2.0 * Tn));
+      g4[0] = w_xy * (sigmoid_precise(r0) - d.offx);
+      g4[1] = w_xy * (sigmoid_precise(r1) - d.offy);
+      g4[2] = w_wh * (2.0f * (r2 - logf(d.w / d.aw + 1e-14f)));
+      g4[3] = w_wh * (2.0f * (r3 - logf(d.h / d.ah + 1e-14f)));
+    }
+    for (int ch = lane; ch < K; ch += 32) {
+      if (ch == 4) continue;  // objectness: written by the dense pass (positive mask)
+      float add;
+      if (ch < 4) {
+        add = ch == 0 ? g4[0] : (ch == 1 ? g4[1] : (ch == 2 ? g4[2] : g4[3]));
+      } else {
+        const float v = ch < 32 ? first : head[nchw_at(p.g, l, self.b, self.a, ch, cell)];
+        add = w_cls * (sigmoid_precise(v) - ((ch - 5 == d.cls) ? 1.0f : 0.0f));
+      }
+      grad[nchw_at(p.g, l, self.b, self.a, ch, cell)] += add;
+    }
+  };
+  for (int b0 = 0; b0 < t; b0 += 32) {
+    const int t2 = b0 + lane;
+    unsigned mk = __ballot_sync(0xffffffffu, t2 < t && keys[t2] == key);
+    while (mk) {
+      const int i = __ffs(mk) - 1;
+      mk &= mk - 1;
+      add_target(b0 + i);
+    }
+  }
+  add_target(t);
+  (void)HW;
+}
+
+static size_t align_up_(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct DemoLayout {
+  size_t key, img_off, img_cur, img_list, tgt_ws, cell_ws, total;
+  int tgt_blocks, cell_ctas;
+};
+
+static DemoLayout demo_layout(const Geom& g, long long T, DemoParams* p) {
+  DemoLayout L;
+  size_t o = 0;
+  L.key = o;      o = align_up_(o + (size_t)g.L * (size_t)(T > 0 ? T : 1) * 4, 256);
+  L.img_off = o;  o = align_up_(o + (size_t)(g.B + 1) * 4, 256);
+  L.img_cur = o;  o = align_up_(o + (size_t)(g.B > 0 ? g.B : 1) * 4, 256);
+  L.img_list = o; o = align_up_(o + (size_t)(T > 0 ? T : 1) * 4, 256);
+  L.tgt_blocks = (int)((T + kTgtThreads / 32 - 1) / (kTgtThreads / 32));
+  L.tgt_ws = o;   o = align_up_(o + (size_t)g.L * (size_t)(L.tgt_blocks > 0 ? L.tgt_blocks : 1) * 4 * 8, 256);
+  int ctas = 0;
+  for (int l = 0; l < g.L; ++l) {
+    const int chunks = (g.A * g.HW[l] + kCellChunk - 1) / kCellChunk;
+    if (p) {
+      p->cell_cta_begin[l] = ctas;
+      p->cell_chunks[l] = chunks;
+    }
+    ctas += chunks * g.B;
+  }
+  if (p)
+    for (int l = g.L; l <= FVB_MAX_LEVELS; ++l) p->cell_cta_begin[l] = ctas;
+  L.cell_ctas = ctas;
+  L.cell_ws = o;  o = align_up_(o + (size_t)(ctas > 0 ? ctas : 1) * 16, 256);
+  L.total = o + 256;
+  return L;
+}
+
+static int demo_common_checks(const Geom& g, const float* const* d_heads, int flavour, const char* who) {
+  FVB_REQUIRE(g.nchw, "%s: heads must be the conv outputs [B,A*K,H,W] (FVB_HEAD_NCHW)", who);
+  FVB_REQUIRE(flavour == FVB_DEMO_LOSS_SHIP || flavour == FVB_DEMO_LOSS_U, "%s: unknown flavour %d", who, flavour);
+  FVB_REQUIRE(g.B >= 1, "%s: empty batch", who);
+  for (int l = 0; l < g.L; ++l) {
+    FVB_REQUIRE(d_heads[l] != nullptr, "%s: head %d is NULL", who, l);
+    FVB_REQUIRE((long long)g.B * g.A * g.HW[l] < (1ll << 31), "%s: level %d has too many boxes for 32-bit keys", who, l);
+  }
+  return FVB_OK;
+}
+
+}  // namespace fvb
+
+using namespace fvb;
+
+extern "C" size_t fvb_demo_loss_workspace_bytes(const fvb_yolo_geom* geom, int64_t num_labels) {
+  Geom g;
+  if (make_geom(geom, nullptr, &g) != FVB_OK) return 0;
+  return demo_layout(g, num_labels, nullptr).total;
+}
+
+extern "C" int64_t fvb_demo_loss_mask_bytes(const fvb_yolo_geom* geom) {
+  Geom g;
+  if (make_geom(geom, nullptr, &g) != FVB_OK) return 0;
+  return (int64_t)g.B * g.row_off[g.L];
+}
+
+extern "C" int fvb_demo_loss_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                 int64_t num_labels, int flavour, double* d_partials, float* d_out, int8_t* d_mask,
+                                 void* d_ws, void* stream) {
+  FVB_REQUIRE(d_heads && d_partials && d_ws, "demo_loss: NULL pointer");
+  FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "demo_loss: num_labels=%lld", (long long)num_labels);
+  FVB_REQUIRE(num_labels == 0 || d_labels, "demo_loss: labels NULL");
+  FVB_REQUIRE(((uintptr_t)d_ws & 255) == 0, "demo_loss: workspace must be 256-byte aligned");
+  DemoParams p;
+  int rc = make_geom(geom, d_heads, &p.g);
+  if (rc != FVB_OK) return rc;
+  rc = demo_common_checks(p.g, d_heads, flavour, "demo_loss");
+  if (rc != FVB_OK) return rc;
+  const DemoLayout L = demo_layout(p.g, num_labels, &p);
+  unsigned char* w = (unsigned char*)d_ws;
+  p.labels = d_labels;
+  p.T = (int)num_labels;
+  p.flavour = flavour;
+  p.key = (int*)(w + L.key);
+  p.img_off = (int*)(w + L.img_off);
+  p.img_cur = (int*)(w + L.img_cur);
+  p.img_list = (int*)(w + L.img_list);
+  p.tgt_ws = (double*)(w + L.tgt_ws);
+  p.cell_ws = (double*)(w + L.cell_ws);
+  p.tgt_blocks = L.tgt_blocks;
+  p.mask = (signed char*)d_mask;
+  for (int l = 0; l < FVB_MAX_LEVELS; ++l) p.mask_off[l] = l < p.g.L ? (long long)p.g.B * p.g.row_off[l] : 0;
+  p.partials = d_partials;
+  p.out = d_out;
+  cudaStream_t s = (cudaStream_t)stream;
+  demo_prep_kernel<<<1, 1024, 0, s>>>(p);
+  count_launch();
+  if (p.T > 0) {
+    dim3 grid((unsigned)L.tgt_blocks, (unsigned)p.g.L);
+    demo_targets_kernel<<<grid, kTgtThreads, 0, s>>>(p);
+    count_launch();
+  }
+  demo_cells_kernel<<<(unsigned)L.cell_ctas, kCellThreads, 0, s>>>(p);
+  demo_finalize_kernel<<<1, 1024, 0, s>>>(p);
+  count_launch(2);
+  return check_launch("demo_loss");
+}
+
+extern "C" int fvb_demo_loss_combine_f32(const fvb_yolo_geom* geom, const double* d_partials, int flavour, float* d_out,
+                                         void* stream) {
+  FVB_REQUIRE(d_partials && d_out, "demo_loss_combine: NULL pointer");
+  DemoCombineParams p;
+  int rc = make_geom(geom, nullptr, &p.g);
+  if (rc != FVB_OK) return rc;
+  FVB_REQUIRE(flavour == FVB_DEMO_LOSS_SHIP || flavour == FVB_DEMO_LOSS_U, "demo_loss_combine: unknown flavour %d", flavour);
+  p.partials = d_partials;
+  p.flavour = flavour;
+  p.out = d_out;
+  demo_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p);
+  count_launch();
+  return check_launch("demo_combine_kernel");
+}
+
+extern "C" int fvb_demo_loss_backward_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                          int64_t num_labels, int flavour, const double* d_partials, const int8_t* d_mask,
+                                          const float* d_grad_out, float* const* d_grad_heads, void* d_ws, void* stream) {
+  FVB_REQUIRE(d_heads && d_partials && d_mask && d_grad_heads && d_ws, "demo_loss_backward: NULL pointer");
+  FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "demo_loss_backward: num_labels=%lld", (long long)num_labels);
+  FVB_REQUIRE(num_labels == 0 || d_labels, "demo_loss_backward: labels NULL");
+  FVB_REQUIRE(((uintptr_t)d_ws & 255) == 0, "demo_loss_backward: workspace must be 256-byte aligned");
+  DemoParams fp;
+  int rc = make_geom(geom, d_heads, &fp.g);
+  if (rc != FVB_OK) return rc;
+  rc = demo_common_checks(fp.g, d_heads, flavour, "demo_loss_backward");
+  if (rc != FVB_OK) return rc;
+  const DemoLayout L = demo_layout(fp.g, num_labels, &fp);
+  unsigned char* w = (unsigned char*)d_ws;
+  fp.labels = d_labels;
+  fp.T = (int)num_labels;
+  fp.flavour = flavour;
+  fp.key = (int*)(w + L.key);
+  fp.img_off = (int*)(w + L.img_off);
+  fp.img_cur = (int*)(w + L.img_cur);
+  fp.img_list = (int*)(w + L.img_list);
+  DemoGradParams p;
+  p.g = fp.g;
+  p.labels = d_labels;
+  p.T = fp.T;
+  p.flavour = flavour;
+  p.key = fp.key;
+  p.mask = (const signed char*)d_mask;
+  p.partials = d_partials;
+  p.grad_out = d_grad_out;
+  bool vec = true;
+  long long ctas = 0;
+  for (int l = 0; l < FVB_MAX_LEVELS; ++l) {
+    p.grad[l] = nullptr;
+    p.lvl_floats[l] = 0;
+    p.mask_off[l] = 0;
+  }
+  for (int l = 0; l < p.g.L; ++l) {
+    FVB_REQUIRE(d_grad_heads[l] != nullptr, "demo_loss_backward: grad %d is NULL", l);
+    p.grad[l] = d_grad_heads[l];
+    p.lvl_floats[l] = (long long)p.g.B * p.g.A * p.g.K * p.g.HW[l];
+    p.mask_off[l] = (long long)p.g.B * p.g.row_off[l];
+    p.cta_begin[l] = (int)ctas;
+    ctas += (p.lvl_floats[l] + kDgChunk - 1) / kDgChunk;
+    if (((uintptr_t)d_grad_heads[l] & 15) != 0) vec = false;
+  }
+  for (int l = p.g.L; l <= FVB_MAX_LEVELS; ++l) p.cta_begin[l] = (int)ctas;
+  FVB_REQUIRE(ctas < (1ll << 31), "demo_loss_backward: tensor too large for one launch");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec) demo_grad_dense_kernel<true><<<(unsigned)ctas, kDgThreads, 0, s>>>(p);
+  else demo_grad_dense_kernel<false><<<(unsigned)ctas, kDgThreads, 0, s>>>(p);
+  count_launch();
+  if (p.T > 0) {
+    demo_prep_kernel<<<1, 1024, 0, s>>>(fp);
+    dim3 grid((unsigned)L.tgt_blocks, (unsigned)p.g.L);
+    demo_grad_targets_kernel<<<grid, kTgtThreads, 0, s>>>(p);
+    count_launch(2);
+  }
+  return check_launch("demo_loss_backward");
+}

@@ -241,6 +241,29 @@ int fvb_bce_loss_backward_f32(const float* d_pre, int64_t rows, int classes, con
                               const float* d_target_val, int already_sigmoid, const float* d_weights, int reduction,
                               const float* d_grad_out, float* d_grad_pre, void* stream);
 
+/* ---- demo training loss ---------------------------------------------------------------------------
+ * ComputeLoss.forward(predict_layers, target_all, model): demos/yolov3_huaweiShip/utils/lossv3.py:19-125 (flavour SHIP,
+ * d_out[3] = loss_box, loss_cls, loss_conf) and demos/yolov3_u/utils/lossv3.py:17-119 (flavour U, d_out[0] = the scalar).
+ * d_heads[l] = the conv outputs [B, A*K, H_l, W_l] (geom->head_layout must be FVB_HEAD_NCHW); anchors in feature units
+ * are geom->anchor_{w,h} / geom->stride (model.anchors with stride 1).  d_labels [T,6] = [batch_idx, cls, xc, yc, w, h].
+ * d_partials [L*6] f64 per level {S_box|S_xy, S_wh, S_cls, S_conf, n_valid, T}: what data-parallel ranks all-reduce before
+ * fvb_demo_loss_combine_f32.  d_mask (optional, [fvb_demo_loss_mask_bytes] int8, level-major [l][b][a][cell]): the
+ * objectness mask (-1 ignore, 0 negative, 1 positive), needed by the backward.  A target whose centre leaves the feature map
+ * is clamped to the border cell (the reference indexes out of range); an image without targets has no ignore region
+ * (the reference raises IndexError at lossv3.py:107 -- the Python wrapper reproduces that when strict). */
+#define FVB_DEMO_LOSS_SHIP 0
+#define FVB_DEMO_LOSS_U 1
+size_t fvb_demo_loss_workspace_bytes(const fvb_yolo_geom* geom, int64_t num_labels);
+int64_t fvb_demo_loss_mask_bytes(const fvb_yolo_geom* geom);
+int fvb_demo_loss_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels, int64_t num_labels,
+                      int flavour, double* d_partials, float* d_out, int8_t* d_mask, void* d_ws, void* stream);
+int fvb_demo_loss_combine_f32(const fvb_yolo_geom* geom, const double* d_partials, int flavour, float* d_out, void* stream);
+/* Gradients w.r.t. the conv outputs (d_grad_heads[l] like d_heads[l], written completely).  d_grad_out: [3] (SHIP: upstream
+ * gradients of the three outputs) or [1] (U), or NULL for ones.  d_ws: fvb_demo_loss_workspace_bytes. */
+int fvb_demo_loss_backward_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                               int64_t num_labels, int flavour, const double* d_partials, const int8_t* d_mask,
+                               const float* d_grad_out, float* const* d_grad_heads, void* d_ws, void* stream);
+
 /* ---- K5 mAP matcher ----------------------------------------------------------------------------
  * CalculateMAP.process_one, metrics/map.py:16-83, for I images in one launch.  d_dets [sum M,6] =
  * [cls, conf, x1,y1,x2,y2], d_det_off [I+1]; d_gts [sum N,5] = [cls, x1,y1,x2,y2], d_gt_off [I+1];

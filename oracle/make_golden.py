@@ -349,10 +349,59 @@ def gold_grads(ns):
     np.savez_compressed(os.path.join(OUT, "grads_small.npz"), **out)
 
 
+def to_nchw(h):
+    """[B,A,H,W,K] -> the conv output layout [B,A*K,H,W] the demos' loss consumes."""
+    b, a, hh, ww, k = h.shape
+    return h.permute(0, 1, 4, 2, 3).reshape(b, a * k, hh, ww).contiguous()
+
+
+def gold_demo_loss(ns):
+    """ComputeLoss of both demos (forward values and autograd gradients w.r.t. the conv outputs) -> tests/golden/demo_loss.npz."""
+    import contextlib
+    import io
+    import types
+    out = {}
+    labels, heads = small_case(13, batch=3)
+    extra = torch.tensor([[1, 2, 0.26, 0.26, 0.3, 0.35],
+                          [1, 3, 0.27, 0.27, 0.31, 0.34],      # same cell, same best anchor as the row above on some levels
+                          [2, 0, 0.5, 0.5, 0.9, 0.8]], dtype=torch.float32)
+    labels = torch.cat([labels, extra], 0)
+    nchw = [to_nchw(h) for h in heads]
+    anchors = [a.reshape(-1, 2) / s for a, s in zip(SMALL.anchors_levels(), SMALL.strides)]
+    model = types.SimpleNamespace(anchors=anchors)
+    out["labels"] = _np(labels)
+    for i, h in enumerate(nchw):
+        out["head%d" % i] = _np(h)
+        out["anchors%d" % i] = _np(anchors[i])
+    ship = ns.load_demo("yolov3_huaweiShip", "lossv3").ComputeLoss()
+    hs = [h.clone().requires_grad_(True) for h in nchw]
+    lb, lc, lo = ship(hs, labels, model)
+    out["ship_box"], out["ship_cls"], out["ship_conf"] = _np(lb), _np(lc), _np(lo)
+    w = torch.tensor([0.05, 0.5, 1.0])
+    out["ship_up"] = _np(w)
+    (lb * w[0] + lc * w[1] + lo * w[2]).sum().backward()
+    for i, h in enumerate(hs):
+        out["ship_grad%d" % i] = _np(h.grad)
+    u = ns.load_demo("yolov3_u", "lossv3").ComputeLoss()
+    hs = [h.clone().requires_grad_(True) for h in nchw]
+    with contextlib.redirect_stdout(io.StringIO()):
+        lu = u(hs, labels, model)
+    out["u_loss"] = _np(lu)
+    (lu * 0.3).sum().backward()
+    out["u_up"] = np.float32(0.3)
+    for i, h in enumerate(hs):
+        out["u_grad%d" % i] = _np(h.grad)
+    np.savez_compressed(os.path.join(OUT, "demo_loss.npz"), **out)
+
+
 def main():
     if "--only-frcnn-nms" in sys.argv:
         torch.set_num_threads(1)
         gold_frcnn_nms(ref_shim.load())
+        return
+    if "--only-demo-loss" in sys.argv:
+        torch.set_num_threads(1)
+        gold_demo_loss(ref_shim.load())
         return
     if "--only-grads" in sys.argv:
         torch.set_num_threads(1)
@@ -368,6 +417,7 @@ def main():
     gold_rpn(ns)
     gold_frcnn_nms(ns)
     gold_grads(ns)
+    gold_demo_loss(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -52,3 +52,8 @@ def T(x):
 @pytest.fixture(scope="session")
 def golden_grads():
     return load_golden("grads_small.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_demo_loss():
+    return load_golden("demo_loss.npz")

@@ -243,3 +243,26 @@ def test_bce_loss_grads(golden_grads):
         GCLOSE(oracle.grad.bce_loss_grad(logits, idx, reduction=red)[1], g["g_bce_%s" % red])
     GCLOSE(oracle.grad.bce_loss_grad(logits.sigmoid(), idx, already_sigmoid=True)[1], g["g_bce_sig_mean"])
     GCLOSE(oracle.grad.bce_loss_grad(T(g["bce1_logits"]), T(g["bce1_tgt"]))[1], g["g_bce1_mean"])
+
+
+# ---- the demos' ComputeLoss (both flavours), values and gradients ---------------------------------------------------------
+def test_demo_compute_loss(golden_demo_loss):
+    g = golden_demo_loss
+    heads = [T(g["head%d" % i]) for i in range(3)]
+    anchors = [T(g["anchors%d" % i]) for i in range(3)]
+    labels = T(g["labels"])
+    hs = [h.clone().requires_grad_(True) for h in heads]
+    lb, lc, lo = oracle.demo_loss.compute_loss(hs, labels, anchors, "ship")
+    CLOSE(lb, g["ship_box"]); CLOSE(lc, g["ship_cls"]); CLOSE(lo, g["ship_conf"])
+    w = g["ship_up"]
+    (lb * float(w[0]) + lc * float(w[1]) + lo * float(w[2])).sum().backward()
+    for i in range(3):
+        GCLOSE(hs[i].grad, g["ship_grad%d" % i])
+    hs = [h.clone().requires_grad_(True) for h in heads]
+    lu = oracle.demo_loss.compute_loss(hs, labels, anchors, "u")
+    CLOSE(lu, g["u_loss"])
+    (lu * float(g["u_up"])).sum().backward()
+    for i in range(3):
+        GCLOSE(hs[i].grad, g["u_grad%d" % i])
+    with pytest.raises(IndexError):                     # an image without targets: lossv3.py:107
+        oracle.demo_loss.compute_loss(heads, labels[labels[:, 0] != 1], anchors, "ship")
