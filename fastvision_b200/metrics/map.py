@@ -1,9 +1,10 @@
 """COCO-style mAP -- drop-in for CalculateMAP, metrics/map.py:6-141.
 
 ``process_one`` keeps the reference signature; ``process_batch`` matches every image of a batch in ONE
-kernel launch (fvb_map_match_f32) without the per-image D2H + numpy argsort/unique.  ``fetch`` is the
-reference's host-side AP integration (float64 numpy, map.py:85-141), restated: per seen class, rows sorted
-by confidence, cumulative TP/FP, precision envelope, 101-point interpolation.
+kernel launch (fvb_map_match_f32) without the per-image D2H + numpy argsort/unique, and keeps the evidence on
+the device.  ``fetch`` runs the AP integration of map.py:85-141 on the device too (fvb_map_ap_f64: radix sort by
+(class, -conf), TP prefix sums, precision envelope, 101-point np.interp + np.trapz in float64) and only brings
+the [classes, thresholds] AP table back for the two final means.
 """
 import ctypes as C
 
@@ -18,8 +19,27 @@ class CalculateMAP:
         self.map_iou_values = np.asarray(map_iou_values, dtype=np.float64)
         if self.map_iou_values.size > 16:
             raise ValueError("at most 16 IoU thresholds")
-        self.correct_all_images = []     # float64 [M, 2 + n_thr] blocks: [conf, cls, correct...]
-        self.seen_all_targets_cls = []
+        self._dets = []          # device [M,6] blocks = [cls, conf, x1,y1,x2,y2]
+        self._correct = []       # device u8 [M, n_thr] blocks
+        self._targets = []       # device f32 target classes
+
+    # the reference's public accumulators (map.py:13-14), materialised on the host on demand
+    @property
+    def correct_all_images(self):
+        """list of float64 [M, 2 + n_thr] blocks [conf, cls, correct...] (one per process_one / process_batch call)."""
+        out = []
+        for d, c in zip(self._dets, self._correct):
+            block = np.zeros([d.size(0), 2 + self.map_iou_values.size], dtype=np.float64)
+            host = d[:, :2].detach().cpu().numpy()
+            block[:, 0] = host[:, 1]
+            block[:, 1] = host[:, 0]
+            block[:, 2:] = c.cpu().numpy()
+            out.append(block)
+        return out
+
+    @property
+    def seen_all_targets_cls(self):
+        return [t.detach().cpu().numpy() for t in self._targets]
 
     # ---- device matcher -------------------------------------------------------------------------------
     def match(self, dets, det_off, gts, gt_off):
@@ -42,18 +62,14 @@ class CalculateMAP:
         return correct
 
     def process_batch(self, dets, det_off, gts, gt_off):
-        """Batched ``process_one``: appends one [sum M, 2+n_thr] block and the target classes of the batch."""
+        """Batched ``process_one``: records the detections, their ``correct`` bits and the target classes (all on the device)."""
         correct = self.match(dets, det_off, gts, gt_off)
-        if gts.size(0):
-            self.seen_all_targets_cls.append(gts[:, 0].detach().cpu().numpy())
-        if dets.size(0) == 0:
+        if gts.size(0):                                   # map.py:43-44
+            self._targets.append(gts[:, 0].detach().contiguous())
+        if dets.size(0) == 0:                             # map.py:46-47
             return
-        block = np.zeros([dets.size(0), 2 + self.map_iou_values.size], dtype=np.float64)
-        host = dets[:, :2].detach().cpu().numpy()
-        block[:, 0] = host[:, 1]
-        block[:, 1] = host[:, 0]
-        block[:, 2:] = correct.cpu().numpy()
-        self.correct_all_images.append(block)
+        self._dets.append(dets.detach())
+        self._correct.append(correct)
 
     def process_one(self, y_pred, y_true):
         """metrics/map.py:16-83.  y_pred[M,6]=[cls,conf,x1,y1,x2,y2]; y_true[N,5]=[cls,x1,y1,x2,y2]."""
@@ -64,40 +80,54 @@ class CalculateMAP:
         gt_off = torch.tensor([0, y_true.size(0)], dtype=torch.int32, device=dev)
         self.process_batch(y_pred, det_off, y_true, gt_off)
 
-    # ---- host AP integration (float64, identical arithmetic to map.py:85-141) -------------------------------
-    @staticmethod
-    def compute_ap(recall, precision, method='coco'):
-        m_recall = np.concatenate(([0.0], recall, [1.0]))
-        m_precision = np.concatenate(([1.0], precision, [0.0]))
-        envelope = np.flip(np.maximum.accumulate(m_precision[::-1]))
-        if method == 'coco':
-            x = np.linspace(0, 1, 101)
-            integrate = getattr(np, "trapezoid", None) or np.trapz
-            return integrate(np.interp(x, m_recall, envelope), x)
-        if method == 'voc2009':
-            i = np.where(m_recall[1:] != m_recall[:-1])[0]
-            return np.sum((m_recall[i + 1] - m_recall[i]) * envelope[i + 1])
-        raise Exception('Not complete')
+    # ---- evidence exchange for data-parallel evaluation (dist.gather_map_state) -----------------------------------------
+    def state(self):
+        """-> (rows [sum M, 2 + n_thr] f32 = [conf, cls, correct...], target classes [sum N] f32), both on the device."""
+        nthr = self.map_iou_values.size
+        if self._dets:
+            d = torch.cat(self._dets)
+            rows = torch.cat([d[:, 1:2], d[:, 0:1], torch.cat(self._correct).float()], dim=1)
+        else:
+            rows = torch.zeros(0, 2 + nthr, device=self._targets[0].device if self._targets else "cuda")
+        tg = torch.cat(self._targets) if self._targets else torch.zeros(0, device=rows.device)
+        return rows, tg
 
-    def _ap_per_class(self, total_positive, correct):
-        ap = np.zeros((len(self.map_iou_values),), dtype=np.float64)
-        tp = np.cumsum(correct, axis=0)
-        fn = total_positive - tp
-        fp = np.cumsum(1 - correct, axis=0)
-        recall = tp / (tp + fn + 1e-16)
-        precision = tp / (tp + fp + 1e-16)
-        for k in range(correct.shape[1]):
-            ap[k] = self.compute_ap(recall[:, k], precision[:, k])
-        return ap
+    def load_state(self, rows, target_cls):
+        """Replace the accumulated evidence by gathered rows / target classes (see ``state``)."""
+        rows = _lib.require_cuda(rows, "rows")
+        dets = torch.zeros(rows.size(0), 6, device=rows.device)
+        dets[:, 0], dets[:, 1] = rows[:, 1], rows[:, 0]
+        self._dets, self._correct = [dets], [rows[:, 2:].to(torch.uint8).contiguous()]
+        self._targets = [_lib.require_cuda(target_cls, "target_cls").contiguous()]
+
+    # ---- AP integration on the device (map.py:85-141) ----------------------------------------------------------------------
+    def ap_table(self):
+        """-> (ap [max_class+1, n_thr] f64 device tensor, NaN rows for unseen classes; pos_count [max_class+2] i32)."""
+        if not self._targets:
+            raise ValueError("need at least one array to concatenate")      # np.concatenate([]) at map.py:124
+        targets = torch.cat(self._targets)
+        dev = targets.device
+        nthr = self.map_iou_values.size
+        if self._dets:
+            dets, correct = torch.cat(self._dets).contiguous(), torch.cat(self._correct).contiguous()
+        else:
+            raise ValueError("need at least one array to concatenate")      # map.py:122
+        max_class = int(targets.max().item())                               # the one sync of fetch (it returns host arrays anyway)
+        if max_class < 0 or max_class >= 65535:
+            raise ValueError("class ids must be integers in [0, 65535)")
+        ap = torch.empty(max_class + 1, nthr, dtype=torch.float64, device=dev)
+        pos = torch.empty(max_class + 2, dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        ws = _lib.workspace(lib.fvb_map_ap_workspace_bytes(dets.size(0), nthr, max_class), dev, "map_ap")
+        with torch.cuda.device(dev):
+            _lib.check(lib.fvb_map_ap_f64(_lib.dptr(dets), _lib.dptr(correct), dets.size(0), _lib.dptr(targets), targets.numel(),
+                                          nthr, max_class, _lib.dptr(ap), _lib.dptr(pos), _lib.dptr(ws), _lib.stream()), "map_ap")
+        return ap, pos
 
     def fetch(self):
         """-> (map_each_iou[n_thr], map_each_cls[n_cls], cls_ids); a class with targets but no detections scores 0.5."""
-        correct = np.concatenate(self.correct_all_images, axis=0)
-        seen = np.concatenate(self.seen_all_targets_cls, axis=0)
-        uniq = np.unique(seen).tolist()
-        table = np.zeros((len(uniq), len(self.map_iou_values)), dtype=np.float64)
-        for i, c in enumerate(uniq):
-            cur = correct[correct[:, 1] == c, ...]
-            cur = cur[np.argsort(-cur[:, 0]), ...]
-            table[i] = self._ap_per_class(np.sum(seen == c), cur[:, 2:])
-        return np.mean(table, axis=0), np.mean(table, axis=1), [int(c) for c in uniq]
+        ap, pos = self.ap_table()
+        ap, pos = ap.cpu().numpy(), pos.cpu().numpy()
+        uniq = [int(c) for c in np.nonzero(pos[:-1] > 0)[0]]                # np.unique(seen) for integer class ids (map.py:125)
+        table = ap[uniq]
+        return np.mean(table, axis=0), np.mean(table, axis=1), uniq         # map.py:138-141

@@ -274,6 +274,19 @@ int fvb_map_match_f32(const float* d_dets, const int32_t* d_det_off, const float
                       int images, int64_t total_dets, const double* thresholds, int n_thr, uint8_t* d_correct,
                       void* d_ws, void* stream);
 
+/* ---- AP integration on the device ---------------------------------------------------------------------
+ * CalculateMAP.fetch / _ap_per_class / compute_ap, metrics/map.py:85-141, without the host numpy pass.
+ * d_dets [n,6] = [cls, conf, ...] (the rows given to fvb_map_match_f32, all images concatenated), d_correct [n, n_thr] u8
+ * (its output), d_target_cls [m] f32 (every target's class).  Class ids are integers in [0, max_class] (< 65535).
+ * d_ap [(max_class+1), n_thr] f64: AP of class c at threshold k, NaN for classes without targets (the reference leaves
+ * them out of the means, map.py:126-127); d_pos_count [max_class+2] i32: targets per class (last slot: other ids).
+ * Rows of equal (class, conf) keep their input order (np.argsort(-conf) at map.py:131 leaves ties unspecified).
+ * float64 arithmetic with numpy's formulas (np.interp, np.trapz); TP/FP counts are exact integers. */
+size_t fvb_map_ap_workspace_bytes(int64_t n_dets, int n_thr, int max_class);
+int fvb_map_ap_f64(const float* d_dets, const uint8_t* d_correct, int64_t n_dets, const float* d_target_cls,
+                   int64_t n_targets, int n_thr, int max_class, double* d_ap, int32_t* d_pos_count, void* d_ws,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

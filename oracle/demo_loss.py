@@ -77,7 +77,7 @@ def compute_loss(predict_layers, target_all, anchor_layers, flavour="ship", part
         t_conf = mask[mask != -1]
         loss_conf += F.binary_cross_entropy_with_logits(p_conf, t_conf)                            # :120
         s_conf = F.binary_cross_entropy_with_logits(p_conf, t_conf, reduction="sum").double()
-        parts.append([float(s_a), float(s_b), float(s_cls), float(s_conf), float(t_conf.numel())])
+        parts.append([float(torch.as_tensor(v).detach()) for v in (s_a, s_b, s_cls, s_conf)] + [float(t_conf.numel())])
     if flavour == "ship":
         out = (loss_box, loss_cls, loss_conf)                                                      # :125
     else:
