@@ -149,6 +149,9 @@ __global__ void labels_grouped_kernel(const float* labels, int T, int* flags) {
   if (threadIdx.x == 0) flags[0] = bad ? 0 : 1;
 }
 
+// Channels of one row held in registers: lane + 32*j, j < kRowRegs (K <= 128); wider rows fall back to read-modify-write.
+constexpr int kRowRegs = 4;
+
 __global__ void __launch_bounds__(kMatchThreads) yolo_grad_match_kernel(const GradParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int TA = p.T * p.g.A;
@@ -159,6 +162,16 @@ __global__ void __launch_bounds__(kMatchThreads) yolo_grad_match_kernel(const Gr
   const TargetCell c = target_cell(p.g, l, p.labels + (size_t)t * 6, a);
   if (!(c.match && c.b >= 0 && c.b < p.g.B)) return;
   const bool grouped = p.flags[0] != 0;
+  const int K = p.g.K, C = K - 5;
+  const size_t rofs = cell_row(p.g, l, c.b, a, c.gy, c.gx) * K;
+  const float* row = p.g.head[l] + rofs;
+  float* grow = p.grad[l] + rofs;
+  const bool in_regs = K <= 32 * kRowRegs;
+
+  // the row is requested before the duplicate scans so that its DRAM latency overlaps them
+  float rv[kRowRegs];
+#pragma unroll
+  for (int j = 0; j < kRowRegs; ++j) rv[j] = (lane + 32 * j < K) ? __ldg(row + lane + 32 * j) : 0.0f;
 
   // loser: a later target of the same image hits the same cell with the same anchor -> that warp owns the row
   for (int t2b = t + 1; t2b < p.T; t2b += 32) {
@@ -177,10 +190,6 @@ __global__ void __launch_bounds__(kMatchThreads) yolo_grad_match_kernel(const Gr
     if (grouped && __all_sync(0xffffffffu, b2 > c.b)) break;
   }
 
-  const int K = p.g.K, C = K - 5;
-  const size_t rofs = cell_row(p.g, l, c.b, a, c.gy, c.gx) * K;
-  const float* row = p.g.head[l] + rofs;
-  float* grow = p.grad[l] + rofs;
   const float gout = upstream(p);
   const double M = p.partials[l * 4 + 3];
   // (loss_box + loss_conf + loss_cls) * bs, ratios applied to the per-level means (yolov3_loss.py:52,58,66-72)
@@ -188,27 +197,49 @@ __global__ void __launch_bounds__(kMatchThreads) yolo_grad_match_kernel(const Gr
   const float w_cls = (float)((double)gout * (double)p.batch_global * (double)p.r_cls / (M * (double)C));
   const float w_conf = conf_coef(p, l, gout);
 
-  const float first = lane < K ? row[lane] : 0.0f;
+  const float first = rv[0];
   const float r0 = __shfl_sync(0xffffffffu, first, 0), r1 = __shfl_sync(0xffffffffu, first, 1);
   const float r2 = __shfl_sync(0xffffffffu, first, 2), r3 = __shfl_sync(0xffffffffu, first, 3);
   const float r4 = __shfl_sync(0xffffffffu, first, 4);
   const float p4 = sigmoid_precise(r4);
   const float g_tgt = w_conf * bce_dt(p4);  // gradient reaching targets_conf[cell]; index_put backward gives it to every duplicate
 
-  // contribution of one match (target t2, same level/anchor/cell) to the row gradient
+  // class-BCE factor of every channel this lane owns: w_cls * p(1-p) * d bce/dp for target 0 and for target 1
+  float acc[kRowRegs], g_neg[kRowRegs], g_pos[kRowRegs];
+#pragma unroll
+  for (int j = 0; j < kRowRegs; ++j) {
+    acc[j] = 0.0f;
+    const float pr = sigmoid_precise(rv[j]);
+    const float dsig = (1.0f - pr) * pr;
+    g_neg[j] = w_cls * (bce_dp(pr, 0.0f) * dsig);
+    g_pos[j] = w_cls * (bce_dp(pr, 1.0f) * dsig);
+  }
+  float conf_grad = 0.0f;
+
+  // contribution of one match (target t2, same level/anchor/cell) to the row gradient: this warp is the row's only
+  // writer after the dense pass (which left zeros there), so the sum is formed in registers, in target order
   auto add_match = [&](int t2, bool self) {
     const TargetCell m = self ? c : target_cell(p.g, l, p.labels + (size_t)t2 * 6, a);
     const MatchRowGrad mg = match_row_grad(r0, r1, r2, r3, m, w_box, g_tgt);
-    const float iou = mg.iou;
-    const float add = lane == 0 ? mg.g[0] : (lane == 1 ? mg.g[1] : (lane == 2 ? mg.g[2] : mg.g[3]));
-    if (lane < 4) grow[lane] += add;
-    if (self && lane == 4) grow[4] = w_conf * (bce_dp(p4, iou) * ((1.0f - p4) * p4));
-    for (int ch = lane; ch < K; ch += 32) {
-      if (ch < 5) continue;
-      const float v = ch < 32 ? first : row[ch];
-      const float pr = sigmoid_precise(v);
-      const float tg = (ch - 5 == m.cls) ? 1.0f : 0.0f;
-      grow[ch] += w_cls * (bce_dp(pr, tg) * ((1.0f - pr) * pr));
+    if (self) conf_grad = w_conf * (bce_dp(p4, mg.iou) * ((1.0f - p4) * p4));
+    if (in_regs) {
+#pragma unroll
+      for (int j = 0; j < kRowRegs; ++j) {
+        const int ch = lane + 32 * j;
+        float add;
+        if (j == 0 && lane < 4) add = lane == 0 ? mg.g[0] : (lane == 1 ? mg.g[1] : (lane == 2 ? mg.g[2] : mg.g[3]));
+        else add = (ch - 5 == m.cls) ? g_pos[j] : g_neg[j];
+        acc[j] += add;
+      }
+    } else {
+      const float add = lane == 0 ? mg.g[0] : (lane == 1 ? mg.g[1] : (lane == 2 ? mg.g[2] : mg.g[3]));
+      if (lane < 4) grow[lane] += add;
+      for (int ch = lane; ch < K; ch += 32) {
+        if (ch < 5) continue;
+        const float pr = sigmoid_precise(row[ch]);
+        const float tg = (ch - 5 == m.cls) ? 1.0f : 0.0f;
+        grow[ch] += w_cls * (bce_dp(pr, tg) * ((1.0f - pr) * pr));
+      }
     }
   };
 
@@ -243,6 +274,15 @@ __global__ void __launch_bounds__(kMatchThreads) yolo_grad_match_kernel(const Gr
     }
   }
   add_match(t, true);
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kRowRegs; ++j) {
+      const int ch = lane + 32 * j;
+      if (ch < K) grow[ch] = ch == 4 ? conf_grad : acc[j];
+    }
+  } else if (lane == 4) {
+    grow[4] = conf_grad;
+  }
 }
 
 // ---- IoU losses and BCE -------------------------------------------------------------------------------------------

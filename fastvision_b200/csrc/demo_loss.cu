@@ -88,9 +88,13 @@ struct DemoParams {
 };
 
 __global__ void __launch_bounds__(1024) demo_prep_kernel(const DemoParams p) {
+  __shared__ int warp_tot[33];
+  __shared__ int carry;
   const int B = p.g.B, T = p.T;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i <= B; i += blockDim.x) p.img_off[i] = 0;
   for (int i = threadIdx.x; i < B; i += blockDim.x) p.img_cur[i] = 0;
+  if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     const float* lab = p.labels + (size_t)t * 6;
@@ -102,24 +106,54 @@ __global__ void __launch_bounds__(1024) demo_prep_kernel(const DemoParams p) {
     }
   }
   __syncthreads();
-  if (threadIdx.x < 32) {  // inclusive scan of the counts, 32 at a time
-    int carry = 0;
-    for (int base = 1; base <= B; base += 32) {
-      const int i = base + threadIdx.x;
-      int v = i <= B ? p.img_off[i] : 0;
+  // inclusive scan of the counts img_off[1..B], 1024 entries per round
+  for (int base = 1; base <= B; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i <= B ? p.img_off[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int tv = warp_tot[lane];
+      int ti = tv;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, v, o);
-        if ((int)threadIdx.x >= o) v += u;
+        const int u = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += u;
       }
-      if (i <= B) p.img_off[i] = v + carry;
-      carry += __shfl_sync(0xffffffffu, v, 31);
+      warp_tot[lane] = ti - tv;
+      if (lane == 31) warp_tot[32] = ti;
     }
+    __syncthreads();
+    if (i <= B) p.img_off[i] = carry + warp_tot[warp] + inc;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_tot[32];
+    __syncthreads();
   }
-  __syncthreads();
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     const int b = (int)p.labels[(size_t)t * 6];
     if (b >= 0 && b < B) p.img_list[p.img_off[b] + atomicAdd(&p.img_cur[b], 1)] = t;
+  }
+  __syncthreads();
+  // the atomic cursors filled every image's list in arbitrary order: sort each (short) list ascending, so that the
+  // duplicate handling of the backward is in target order
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int* lst = p.img_list + p.img_off[b];
+    const int n = p.img_off[b + 1] - p.img_off[b];
+    for (int i = 1; i < n; ++i) {
+      const int v = lst[i];
+      int j = i - 1;
+      while (j >= 0 && lst[j] > v) {
+        lst[j + 1] = lst[j];
+        --j;
+      }
+      lst[j + 1] = v;
+    }
   }
 }
 
@@ -181,9 +215,16 @@ __global__ void __launch_bounds__(kTgtThreads) demo_targets_kernel(const DemoPar
   }
 }
 
+// objectness BCE-with-logits of the dense stream: MUFU ex2 for exp(-|x|) (2^-22 relative), exact log1pf
+__device__ __forceinline__ float bce_logits_stream(float x, float t) {
+  const float e = ex2_approx(-fabsf(x) * kLog2e);
+  return (1.0f - t) * x - (fminf(x, 0.0f) - log1pf(e));
+}
+
 __global__ void __launch_bounds__(kCellThreads) demo_cells_kernel(const DemoParams p) {
   __shared__ Box s_box[kStage];
   __shared__ int s_key[kStage];
+  __shared__ float s_aw[FVB_MAX_ANCHORS], s_ah[FVB_MAX_ANCHORS];
   __shared__ double scratch[32];
   int l = 0;
 #pragma unroll
@@ -194,27 +235,30 @@ __global__ void __launch_bounds__(kCellThreads) demo_cells_kernel(const DemoPara
   const int HW = p.g.HW[l], W = p.g.W[l], K = p.g.K;
   const int boxes = p.g.A * HW;
   const float* __restrict__ head = p.g.head[l] + (size_t)b * p.g.A * K * HW;
+  if ((int)threadIdx.x < p.g.A) {
+    s_aw[threadIdx.x] = p.g.aw[l][threadIdx.x] / p.g.stride[l];
+    s_ah[threadIdx.x] = p.g.ah[l][threadIdx.x] / p.g.stride[l];
+  }
 
-  // this thread's boxes: decode (lossv3.py:65-69) and keep xyxy + objectness logit
-  Box pb[kCellBoxes];
-  float conf[kCellBoxes];
-  float best[kCellBoxes];
-  bool pos[kCellBoxes];
+  // this thread's boxes: objectness logit now; the box itself only if some target can reach IoU > 0.5 with it
+  int ja[kCellBoxes], jcell[kCellBoxes];
+  float conf[kCellBoxes], cgx[kCellBoxes], cgy[kCellBoxes];
+  bool pos[kCellBoxes], ign[kCellBoxes], cand[kCellBoxes];
 #pragma unroll
   for (int q = 0; q < kCellBoxes; ++q) {
     const int j = chunk * kCellChunk + q * kCellThreads + threadIdx.x;
-    best[q] = -1.0f;
-    pos[q] = false;
+    pos[q] = ign[q] = cand[q] = false;
     conf[q] = 0.0f;
-    pb[q].x1 = pb[q].y1 = pb[q].x2 = pb[q].y2 = 0.0f;
+    ja[q] = jcell[q] = 0;
+    cgx[q] = cgy[q] = 0.0f;
     if (j < boxes) {
       const int a = j / HW, cell = j - a * HW;
-      const int gy = cell / W, gx = cell - gy * W;
-      const float* q0 = head + (size_t)a * K * HW + cell;
-      const float t0 = __ldg(q0), t1 = __ldg(q0 + HW), t2 = __ldg(q0 + 2 * (size_t)HW), t3 = __ldg(q0 + 3 * (size_t)HW);
-      conf[q] = __ldg(q0 + 4 * (size_t)HW);
-      const float aw = p.g.aw[l][a] / p.g.stride[l], ah = p.g.ah[l][a] / p.g.stride[l];
-      pb[q] = xywh_to_xyxy(sigmoid_precise(t0) + (float)gx, sigmoid_precise(t1) + (float)gy, expf(t2) * aw, expf(t3) * ah);
+      const int gy = cell / W;
+      ja[q] = a;
+      jcell[q] = cell;
+      cgx[q] = (float)(cell - gy * W);
+      cgy[q] = (float)gy;
+      conf[q] = __ldg(head + ((size_t)a * K + 4) * HW + cell);
     }
   }
   // targets of image b, kStage at a time
@@ -231,15 +275,42 @@ __global__ void __launch_bounds__(kCellThreads) demo_cells_kernel(const DemoPara
       s_key[threadIdx.x] = key >= 0 ? key - key_base : -1;
     }
     __syncthreads();
-    for (int i = 0; i < ns; ++i) {
-      const Box tb = s_box[i];
-      const int tk = s_key[i];
+    // IoU > 0.5 needs the intersection to cover more than half of each box, hence more than half of the predicted box's
+    // width and height: its centre (sigmoid + cell, inside [g, g+1]) must lie inside the target box.  Cells that no target
+    // box touches skip the four box planes and all transcendental math (exact: the test is conservative).
 #pragma unroll
-      for (int q = 0; q < kCellBoxes; ++q) {
-        const float v = iou_plain<false>(pb[q], tb, 1e-7f);  // xywh_iou_batch (lossv3.py:106)
-        best[q] = fmaxf(best[q], v);
-        pos[q] = pos[q] || (tk == chunk * kCellChunk + q * kCellThreads + (int)threadIdx.x);
+    for (int q = 0; q < kCellBoxes; ++q) {
+      const int j = chunk * kCellChunk + q * kCellThreads + threadIdx.x;
+      bool c = false;
+      for (int i = 0; i < ns; ++i) {
+        const Box tb = s_box[i];
+        c = c || (cgx[q] <= tb.x2 && cgx[q] + 1.0f >= tb.x1 && cgy[q] <= tb.y2 && cgy[q] + 1.0f >= tb.y1);
+        pos[q] = pos[q] || (s_key[i] == j);
       }
+      cand[q] = c && j < boxes && !ign[q];
+    }
+#pragma unroll
+    for (int q = 0; q < kCellBoxes; ++q) {
+      if (!cand[q]) continue;
+      const float* q0 = head + (size_t)ja[q] * K * HW + jcell[q];
+      const float t0 = __ldg(q0), t1 = __ldg(q0 + HW), t2 = __ldg(q0 + 2 * (size_t)HW), t3 = __ldg(q0 + 3 * (size_t)HW);
+      // lossv3.py:65-69
+      const Box pb = xywh_to_xyxy(sigmoid_precise(t0) + cgx[q], sigmoid_precise(t1) + cgy[q], expf(t2) * s_aw[ja[q]],
+                                  expf(t3) * s_ah[ja[q]]);
+      const float area_p = (pb.x2 - pb.x1) * (pb.y2 - pb.y1);
+      bool hit = false;
+      for (int i = 0; i < ns && !hit; ++i) {
+        const Box tb = s_box[i];
+        const float inter = inter_area(pb, tb);
+        if (inter > 0.0f) {
+          // xywh_iou_batch (lossv3.py:106): inter / (area_p + area_t - inter + eps) > 0.5 (:110); the division is only
+          // evaluated inside a guard band around the threshold
+          const float uni = ((area_p + (tb.x2 - tb.x1) * (tb.y2 - tb.y1)) - inter) + 1e-7f;
+          if (inter > 0.5000005f * uni) hit = true;
+          else if (inter >= 0.4999995f * uni) hit = inter / uni > 0.5f;
+        }
+      }
+      ign[q] = hit;
     }
   }
   double sum = 0.0, cnt = 0.0;
@@ -248,10 +319,10 @@ __global__ void __launch_bounds__(kCellThreads) demo_cells_kernel(const DemoPara
     const int j = chunk * kCellChunk + q * kCellThreads + threadIdx.x;
     if (j < boxes) {
       // mask: -1 ignore (max IoU > 0.5, lossv3.py:110), then positives overwrite with 1 (:115)
-      const signed char m = pos[q] ? 1 : (best[q] > 0.5f ? -1 : 0);
+      const signed char m = pos[q] ? 1 : (ign[q] ? -1 : 0);
       if (p.mask) p.mask[p.mask_off[l] + (long long)b * boxes + j] = m;
       if (m >= 0) {
-        sum += (double)bce_logits(conf[q], (float)m);  // :118-120
+        sum += (double)bce_logits_stream(conf[q], (float)m);  // :118-120
         cnt += 1.0;
       }
     }
@@ -297,9 +368,20 @@ __global__ void __launch_bounds__(1024) demo_finalize_kernel(const DemoParams p)
 #pragma unroll
       for (int c = 0; c < 4; ++c) v[c] += p.tgt_ws[((size_t)l * p.tgt_blocks + i) * 4 + c];
     double cs = 0.0, cn = 0.0;
-    for (int i = p.cell_cta_begin[l] + threadIdx.x; i < p.cell_cta_begin[l + 1]; i += blockDim.x) {
-      cs += p.cell_ws[(size_t)i * 2];
-      cn += p.cell_ws[(size_t)i * 2 + 1];
+    {
+      const double2* cw = reinterpret_cast<const double2*>(p.cell_ws);
+      const int e = p.cell_cta_begin[l + 1], st = blockDim.x;
+      int i = p.cell_cta_begin[l] + threadIdx.x;
+      for (; i + 3 * st < e; i += 4 * st) {  // four independent 16-byte loads in flight
+        const double2 a = cw[i], b2 = cw[i + st], c2 = cw[i + 2 * st], d2 = cw[i + 3 * st];
+        cs += (a.x + b2.x) + (c2.x + d2.x);
+        cn += (a.y + b2.y) + (c2.y + d2.y);
+      }
+      for (; i < e; i += st) {
+        const double2 a = cw[i];
+        cs += a.x;
+        cn += a.y;
+      }
     }
     double r[6];
 #pragma unroll
@@ -332,6 +414,8 @@ struct DemoGradParams {
   const float* labels;
   int T, flavour;
   const int* key;             // [L][T] (demo_prep)
+  const int* img_off;         // [B+1] per-image target lists, ascending target ids (demo_prep)
+  const int* img_list;
   const signed char* mask;    // forward's mask
   long long mask_off[FVB_MAX_LEVELS];
   const double* partials;     // [L][kDemoParts] (all-reduced under data parallelism)
@@ -420,11 +504,6 @@ __global__ void __launch_bounds__(kTgtThreads) demo_grad_targets_kernel(const De
   const int* keys = p.key + (size_t)l * p.T;
   const int key = keys[t];
   if (key < 0) return;
-  // the last target of a (cell, anchor) owns the row; earlier duplicates are added by it in target order
-  for (int b0 = t + 1; b0 < p.T; b0 += 32) {
-    const int t2 = b0 + lane;
-    if (__any_sync(0xffffffffu, t2 < p.T && keys[t2] == key)) return;
-  }
   const DemoTarget self = demo_target(p.g, l, p.labels + (size_t)t * 6);
   const int K = p.g.K, C = K - 5, HW = p.g.HW[l];
   const int cell = self.gy * p.g.W[l] + self.gx;
@@ -433,7 +512,27 @@ __global__ void __launch_bounds__(kTgtThreads) demo_grad_targets_kernel(const De
   const double Tn = p.partials[l * kDemoParts + 5];
   const float w_cls = (float)((double)demo_up(p, 1) / (Tn * C));
   const float w_box = (float)((double)demo_up(p, 0) / Tn);
-  const float first = lane < K ? head[nchw_at(p.g, l, self.b, self.a, lane, cell)] : 0.0f;
+  constexpr int kRegs = 4;  // channels lane + 32*j of the row kept in registers (K <= 128); wider rows read-modify-write
+  const bool in_regs = K <= 32 * kRegs;
+  float rv[kRegs], sg[kRegs], acc[kRegs];
+#pragma unroll
+  for (int j = 0; j < kRegs; ++j) rv[j] = (lane + 32 * j < K) ? __ldg(head + nchw_at(p.g, l, self.b, self.a, lane + 32 * j, cell)) : 0.0f;
+  // (the row is requested before the duplicate scan so that its DRAM latency overlaps it)
+  // Duplicates of a (cell, anchor) live in the same image: only that image's (sorted) target list is scanned.  The last
+  // target of the key owns the row; earlier duplicates are added by it in target order.
+  const int img = (int)p.labels[(size_t)t * 6];
+  const int lb = p.img_off[img], le = p.img_off[img + 1];
+  for (int b0 = lb; b0 < le; b0 += 32) {
+    const int i = b0 + lane;
+    const int t2 = i < le ? p.img_list[i] : -1;
+    if (__any_sync(0xffffffffu, t2 > t && keys[t2] == key)) return;
+  }
+#pragma unroll
+  for (int j = 0; j < kRegs; ++j) {
+    sg[j] = sigmoid_precise(rv[j]);
+    acc[j] = 0.0f;
+  }
+  const float first = rv[0];
   const float r0 = __shfl_sync(0xffffffffu, first, 0), r1 = __shfl_sync(0xffffffffu, first, 1);
   const float r2 = __shfl_sync(0xffffffffu, first, 2), r3 = __shfl_sync(0xffffffffu, first, 3);
 
@@ -460,28 +559,47 @@ __global__ void __launch_bounds__(kTgtThreads) demo_grad_targets_kernel(const De
       g4[2] = w_wh * (2.0f * (r2 - logf(d.w / d.aw + 1e-14f)));
       g4[3] = w_wh * (2.0f * (r3 - logf(d.h / d.ah + 1e-14f)));
     }
-    for (int ch = lane; ch < K; ch += 32) {
-      if (ch == 4) continue;  // objectness: written by the dense pass (positive mask)
-      float add;
-      if (ch < 4) {
-        add = ch == 0 ? g4[0] : (ch == 1 ? g4[1] : (ch == 2 ? g4[2] : g4[3]));
-      } else {
-        const float v = ch < 32 ? first : head[nchw_at(p.g, l, self.b, self.a, ch, cell)];
-        add = w_cls * (sigmoid_precise(v) - ((ch - 5 == d.cls) ? 1.0f : 0.0f));
+    if (in_regs) {
+      // this warp is the only writer of the row after the dense pass (zeros there): sum in registers, in target order
+#pragma unroll
+      for (int j = 0; j < kRegs; ++j) {
+        const int ch = lane + 32 * j;
+        float add;
+        if (j == 0 && lane < 4) add = lane == 0 ? g4[0] : (lane == 1 ? g4[1] : (lane == 2 ? g4[2] : g4[3]));
+        else add = w_cls * (sg[j] - ((ch - 5 == d.cls) ? 1.0f : 0.0f));
+        acc[j] += add;
       }
-      grad[nchw_at(p.g, l, self.b, self.a, ch, cell)] += add;
+    } else {
+      for (int ch = lane; ch < K; ch += 32) {
+        if (ch == 4) continue;  // objectness: written by the dense pass (positive mask)
+        float add;
+        if (ch < 4) {
+          add = ch == 0 ? g4[0] : (ch == 1 ? g4[1] : (ch == 2 ? g4[2] : g4[3]));
+        } else {
+          add = w_cls * (sigmoid_precise(head[nchw_at(p.g, l, self.b, self.a, ch, cell)]) - ((ch - 5 == d.cls) ? 1.0f : 0.0f));
+        }
+        grad[nchw_at(p.g, l, self.b, self.a, ch, cell)] += add;
+      }
     }
   };
-  for (int b0 = 0; b0 < t; b0 += 32) {
-    const int t2 = b0 + lane;
-    unsigned mk = __ballot_sync(0xffffffffu, t2 < t && keys[t2] == key);
+  for (int b0 = lb; b0 < le; b0 += 32) {
+    const int i = b0 + lane;
+    const int t2 = i < le ? p.img_list[i] : -1;
+    unsigned mk = __ballot_sync(0xffffffffu, t2 >= 0 && t2 < t && keys[t2] == key);
     while (mk) {
-      const int i = __ffs(mk) - 1;
+      const int src = __ffs(mk) - 1;
       mk &= mk - 1;
-      add_target(b0 + i);
+      add_target(__shfl_sync(0xffffffffu, t2, src));
     }
   }
   add_target(t);
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kRegs; ++j) {
+      const int ch = lane + 32 * j;
+      if (ch < K && ch != 4) grad[nchw_at(p.g, l, self.b, self.a, ch, cell)] = acc[j];
+    }
+  }
   (void)HW;
 }
 
@@ -629,6 +747,8 @@ extern "C" int fvb_demo_loss_backward_f32(const fvb_yolo_geom* geom, const float
   p.T = fp.T;
   p.flavour = flavour;
   p.key = fp.key;
+  p.img_off = fp.img_off;
+  p.img_list = fp.img_list;
   p.mask = (const signed char*)d_mask;
   p.partials = d_partials;
   p.grad_out = d_grad_out;

@@ -169,3 +169,37 @@ def test_backward_full_size_properties_b256():
         want = coef * p * (1 - p) / (1 - p + 1e-8)
         sel = ~nz_rows
         torch.testing.assert_close(gr[..., 4][sel].double(), want[sel], rtol=2e-5, atol=1e-12)
+
+
+def test_backward_wide_rows_fallback_path():
+    """K = 5 + 140 > 128 channels: the matched-row kernels leave the register path and read-modify-write the row."""
+    cfg = synth.YoloConfig("wide", 64, 140, [[40, 30], [50, 60], [30, 50], [20, 24], [16, 10], [12, 22], [4, 6], [8, 5], [7, 9]],
+                           labels_per_img=4.0, max_labels=9)
+    batch = 2
+    g = synth.make_generator(5)
+    labels = synth.make_labels(cfg, batch, g)
+    dup = labels[:2].clone()
+    dup[:, 1] = (dup[:, 1] + 3) % cfg.num_classes
+    labels = torch.cat([labels, dup], 0)
+    labels = labels[torch.argsort(labels[:, 0], stable=True)]
+    heads = synth.make_heads(cfg, batch, labels, g)
+    _, want = oracle.grad.yolov3_loss_grad(heads, labels, cfg.anchors_levels(), cfg.strides)
+    lossf = fl.Yolov3Loss(_Model(cfg), 0.5, 0.05, 1.0, 0.5)
+    dh = [h.cuda().requires_grad_(True) for h in heads]
+    lossf(dh, labels.cuda()).sum().backward()
+    for i in range(3):
+        gclose(dh[i].grad, want[i])
+    # the demos' loss on the same wide head
+    import types
+    from fastvision_b200.loss import ComputeLoss
+    nchw = [h.permute(0, 1, 4, 2, 3).reshape(h.size(0), -1, h.size(2), h.size(3)).contiguous() for h in heads]
+    anchors = [a.reshape(-1, 2) / s for a, s in zip(cfg.anchors_levels(), cfg.strides)]
+    hs = [h.clone().requires_grad_(True) for h in nchw]
+    lb, lc, lo = oracle.demo_loss.compute_loss(hs, labels, anchors, "ship")
+    (lb + lc + lo).sum().backward()
+    dn = [h.cuda().requires_grad_(True) for h in nchw]
+    gb, gc, go = ComputeLoss()(dn, labels.cuda(), types.SimpleNamespace(anchors=anchors))
+    close(gb, lb); close(gc, lc); close(go, lo)
+    (gb + gc + go).sum().backward()
+    for i in range(3):
+        gclose(dn[i].grad, hs[i].grad)
