@@ -79,6 +79,8 @@ _SIGS = {
                                              C.POINTER(_P), _P, _P]),
     "fvb_map_match_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "fvb_map_match_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int, _P, _P, _P]),
+    "fvb_demo_boxes_postprocess_f32": (C.c_int, [_P, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                                 C.c_float, _P]),
     "fvb_map_ap_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "fvb_map_ap_f64": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P]),
 }

@@ -1,0 +1,7 @@
+"""Drop-in for the hot-path part of demos/yolov3_u/inference.py: ``postProcess`` (:55-121, YOLOv5 decode form :86-89)."""
+from ..postprocess import post_process
+
+
+def postProcess(predict_layers, strides, anchors, conf_thres, iou_thres, resize_ratio, padding_left, padding_top, ori_width, ori_height):
+    return post_process(predict_layers, strides, anchors, conf_thres, iou_thres, resize_ratio, padding_left, padding_top,
+                        ori_width, ori_height, form="v5")

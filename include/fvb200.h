@@ -140,6 +140,15 @@ int fvb_bce_loss_f32(const float* d_pre, int64_t rows, int classes, const int64_
                      const float* d_target_val, int already_sigmoid, const float* d_weights, int reduction,
                      float* d_out, void* d_ws, void* stream);
 
+/* ---- demo box post-processing -------------------------------------------------------------------------------------
+ * The part of the demos' postProcess between decode and NMS (demos/yolov3_u/inference.py:92-109, identical in
+ * demos/yolov3_huaweiShip/inference.py:112-129), in place on decoded rows [n_rows, channels] (xywh in channels 0..3):
+ * x,y,w,h -> ((x - pad_left)/ratio, (y - pad_top)/ratio, w/ratio, h/ratio); clamp to the original image; rows with
+ * w <= min_wh or h <= min_wh (5 px in the demos) are marked dropped (objectness := -1, they keep their slot so the order
+ * of the others is unchanged); xywh -> xyxy; clamp to [0, ori-1].  Follow with fvb_yolo_nms_f32(flavour FVB_NMS_DEMO). */
+int fvb_demo_boxes_postprocess_f32(float* d_rows, int64_t n_rows, int channels, float pad_left, float pad_top,
+                                   float resize_ratio, float ori_width, float ori_height, float min_wh, void* stream);
+
 /* ---- K3 NMS --------------------------------------------------------------------------------
  * fvb_nms_segmented_f32: the batched equivalent of torchvision.ops.nms (third party; call sites
  * detection/tools/NMS.py:18, demos/yolov3_u/utils/nms.py:47,92, demos/faster_rcnn/models/rpn.py:198).

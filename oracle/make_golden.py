@@ -394,6 +394,40 @@ def gold_demo_loss(ns):
     np.savez_compressed(os.path.join(OUT, "demo_loss.npz"), **out)
 
 
+def _ref_function(path, name, namespace):
+    """Compile ONE function of a reference file (unmodified source text) in ``namespace``: the demo scripts import cv2 /
+    albumentations at module level and cannot be imported as a whole here."""
+    import ast
+    src = open(path).read()
+    tree = ast.parse(src)
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+    exec(code, namespace)
+    return namespace[name]
+
+
+def gold_postprocess(ns):
+    """demos/<x>/inference.py postProcess (decode + un-letterbox + filter + class-aware NMS), both demos -> tests/golden/postprocess.npz."""
+    out = {}
+    labels, heads = small_case(17, batch=1)
+    nchw = [to_nchw(h) for h in heads]
+    anchors = [a.reshape(-1, 2) / s for a, s in zip(SMALL.anchors_levels(), SMALL.strides)]
+    args = dict(conf_thres=0.2, iou_thres=0.4, resize_ratio=0.8, padding_left=3, padding_top=5, ori_width=72, ori_height=66)
+    for i, h in enumerate(nchw):
+        out["head%d" % i] = _np(h)
+        out["anchors%d" % i] = _np(anchors[i])
+    out["args"] = np.array([args[k] for k in ("conf_thres", "iou_thres", "resize_ratio", "padding_left", "padding_top", "ori_width", "ori_height")],
+                           dtype=np.float64)
+    for demo in ("yolov3_u", "yolov3_huaweiShip"):
+        box = ns.load_demo(demo, "box")
+        nms = ns.load_demo(demo, "nms")
+        env = {"torch": torch, "grid": box.grid, "xywh2xyxy": box.xywh2xyxy, "non_max_suppression": nms.non_max_suppression}
+        fn = _ref_function(os.path.join(ref_shim.REFERENCE_ROOT, "demos", demo, "inference.py"), "postProcess", env)
+        scores, cats, boxes = fn([h.clone() for h in nchw], SMALL.strides, anchors, **args)
+        out[demo + "_scores"], out[demo + "_cats"], out[demo + "_boxes"] = _np(scores), _np(cats), _np(boxes)
+    np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **out)
+
+
 def main():
     if "--only-frcnn-nms" in sys.argv:
         torch.set_num_threads(1)
@@ -402,6 +436,10 @@ def main():
     if "--only-demo-loss" in sys.argv:
         torch.set_num_threads(1)
         gold_demo_loss(ref_shim.load())
+        return
+    if "--only-postprocess" in sys.argv:
+        torch.set_num_threads(1)
+        gold_postprocess(ref_shim.load())
         return
     if "--only-grads" in sys.argv:
         torch.set_num_threads(1)
@@ -418,6 +456,7 @@ def main():
     gold_frcnn_nms(ns)
     gold_grads(ns)
     gold_demo_loss(ns)
+    gold_postprocess(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

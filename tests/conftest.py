@@ -57,3 +57,8 @@ def golden_grads():
 @pytest.fixture(scope="session")
 def golden_demo_loss():
     return load_golden("demo_loss.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_postprocess():
+    return load_golden("postprocess.npz")

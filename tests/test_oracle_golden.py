@@ -266,3 +266,15 @@ def test_demo_compute_loss(golden_demo_loss):
         GCLOSE(hs[i].grad, g["u_grad%d" % i])
     with pytest.raises(IndexError):                     # an image without targets: lossv3.py:107
         oracle.demo_loss.compute_loss(heads, labels[labels[:, 0] != 1], anchors, "ship")
+
+
+# ---- the demos' postProcess (decode + un-letterbox + min-size filter + class-aware NMS) -----------------------------------
+@pytest.mark.parametrize("demo,form", [("yolov3_u", "v5"), ("yolov3_huaweiShip", "v3")])
+def test_demo_postprocess(golden_postprocess, demo, form):
+    g = golden_postprocess
+    heads = [T(g["head%d" % i]) for i in range(3)]
+    anchors = [T(g["anchors%d" % i]) for i in range(3)]
+    ct, it, rr, pl, pt, ow, oh = g["args"].tolist()
+    s, c, b, _ = oracle.postprocess.post_process(heads, SMALL.strides, anchors, ct, it, rr, int(pl), int(pt), int(ow), int(oh), form)
+    CLOSE(s, g[demo + "_scores"]); CLOSE(b, g[demo + "_boxes"])
+    assert np.array_equal(c.numpy(), g[demo + "_cats"])
