@@ -1,0 +1,108 @@
+"""BASELINE.json configs[2] and configs[4] on one GPU (CUDA events): YOLOv3-608 few-class decode+NMS+loss, and the
+mAP@[.5:.95] evaluation over 5000 synthetic images (batched matcher + device AP integration), with the oracle's host
+numpy fetch timed beside the latter on the same evidence."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fastvision_b200 import synth  # noqa: E402
+from fastvision_b200.metrics import CalculateMAP  # noqa: E402
+from fastvision_b200.pipeline import ValStep  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--ship-batch", type=int, default=1024)
+ap.add_argument("--map-images", type=int, default=5000)
+ap.add_argument("--map-batch", type=int, default=250)
+args = ap.parse_args()
+out = {}
+
+
+def events():
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+# ---- configs[2]: YOLOv3-608, 10 classes ------------------------------------------------------------------------------
+cfg = synth.SHIP608
+g = synth.make_generator(3)
+labels = synth.make_labels(cfg, args.ship_batch, g)
+heads = synth.make_heads(cfg, args.ship_batch, labels, g)
+dh, dl = [h.cuda() for h in heads], labels.cuda()
+del heads
+step = ValStep(cfg.anchors_levels(), cfg.strides)
+step(dh, dl)
+replay = step.capture(dh, dl)
+for _ in range(5):
+    replay()
+torch.cuda.synchronize()
+a, b = events()
+a.record()
+for _ in range(30):
+    replay()
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 30
+alg = 2 * args.ship_batch * step.ctx.rows * step.ctx.k * 4
+out["config3_ship608"] = {"batch": args.ship_batch, "ms_per_step": ms, "images_per_s": args.ship_batch / ms * 1e3,
+                          "algorithmic_GBps": alg / ms / 1e6, "kept_mean": step.out["cnt"].float().mean().item()}
+print(out["config3_ship608"], flush=True)
+del dh, step, replay
+torch.cuda.empty_cache()
+
+# ---- configs[4]: mAP over 5000 images -----------------------------------------------------------------------------------
+cfg = synth.COCO416
+thr = np.linspace(0.5, 0.95, 10)
+est = CalculateMAP(thr)
+step = ValStep(cfg.anchors_levels(), cfg.strides)
+t_match = 0.0
+n_dets = 0
+for i0 in range(0, args.map_images, args.map_batch):
+    gb = synth.make_generator(5, i0)
+    lab = synth.make_labels(cfg, args.map_batch, gb)
+    hd = [h.cuda() for h in synth.make_heads(cfg, args.map_batch, lab, gb)]
+    o = step(hd, lab.cuda())
+    cnt = o["cnt"].long()
+    det_off = torch.zeros(args.map_batch + 1, dtype=torch.int32, device="cuda")
+    det_off[1:] = torch.cumsum(cnt, 0).int()
+    valid = torch.arange(o["boxes"].size(1), device="cuda")[None, :] < cnt[:, None]
+    dets = torch.cat([o["cls"].float().unsqueeze(-1), o["scores"].unsqueeze(-1), o["boxes"]], 2)[valid].contiguous()
+    gts, goff = [], [0]
+    for j in range(args.map_batch):
+        tj = synth.labels_to_pixel_targets(lab, j, cfg.img, cfg.img)
+        gts.append(tj)
+        goff.append(goff[-1] + tj.size(0))
+    gts = torch.cat(gts).cuda()
+    goff = torch.tensor(goff, dtype=torch.int32, device="cuda")
+    a, b = events()
+    a.record()
+    est.process_batch(dets, det_off, gts, goff)
+    b.record()
+    torch.cuda.synchronize()
+    t_match += a.elapsed_time(b)
+    n_dets += dets.size(0)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+m_iou, m_cls, ids = est.fetch()
+torch.cuda.synchronize()
+t_fetch = (time.perf_counter() - t0) * 1e3
+t0 = time.perf_counter()
+m_iou, m_cls, ids = est.fetch()
+t_fetch2 = (time.perf_counter() - t0) * 1e3
+import oracle  # noqa: E402  (the checker, timed as the host baseline of this step)
+ora = oracle.map_.MapOracle(thr)
+ora.correct_all_images, ora.seen_all_targets_cls = est.correct_all_images, est.seen_all_targets_cls
+t0 = time.perf_counter()
+w_iou, w_cls, w_ids = ora.fetch()
+t_host = (time.perf_counter() - t0) * 1e3
+out["config5_map"] = {"images": args.map_images, "detections": n_dets, "match_ms_total": t_match,
+                      "fetch_device_ms_first": t_fetch, "fetch_device_ms": t_fetch2, "fetch_host_numpy_ms": t_host,
+                      "mAP50": float(m_iou[0]), "mAP50_95": float(m_iou.mean()),
+                      "max_abs_diff_vs_host": float(np.abs(m_iou - w_iou).max()), "classes": len(ids)}
+print(out["config5_map"], flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/config_bench.json", "w"), indent=1)
