@@ -3,7 +3,7 @@
 // cumulative TP/FP sums, the precision envelope and a 101-point interpolation -- O(sum M log sum M) of numpy on <= 1.5 M
 // rows at BASELINE configs[4].  Here:
 //   ap_keys      : key = (class << 32) | descending-orderable(conf), payload = row index
-//   radix passes : global stable LSD radix sort, 8-bit digits (per-tile histogram -> one-CTA scan -> stable scatter with the
+//   radix passes : global stable LSD radix sort, 8-bit digits (per-tile histogram -> per-digit row scans -> stable scatter with the
 //                  warp match.any multisplit of nms.cuh); 4 passes for the confidence bits + 1-2 for the class bits
 //   ap_segments  : class segment boundaries in the sorted order; ap_targets: positives per class (integer atomics)
 //   ap_class     : one CTA per (class, IoU threshold): TP prefix sums, precision, right-to-left envelope, the 101
@@ -43,7 +43,8 @@ struct SortParams {
   uint32_t* dst_idx;
   long long n;
   int shift, nblocks;
-  uint32_t* hist;  // [256][nblocks]
+  uint32_t* hist;    // [256][nblocks]
+  uint32_t* totals;  // [256]
 };
 
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const SortParams p) {
@@ -59,16 +60,18 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const SortParam
   if (threadIdx.x < 256) p.hist[(size_t)threadIdx.x * p.nblocks + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// exclusive scan of hist (digit-major) in place, one CTA
-__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* hist, int total) {
-  __shared__ uint32_t warp_tot[33];
+// One CTA per digit: exclusive scan of the digit's row hist[d][0..nblocks) in place, row total -> totals[d].  The scatter
+// kernel adds the exclusive scan of the 256 totals itself (a single-CTA scan of all 256*nblocks entries took 87 us per pass).
+__global__ void __launch_bounds__(256) sort_scan_kernel(uint32_t* hist, int nblocks, uint32_t* totals) {
+  __shared__ uint32_t warp_tot[9];
   __shared__ uint32_t carry;
+  uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < total; base += 1024) {
+  for (int base = 0; base < nblocks; base += 256) {
     const int i = base + threadIdx.x;
-    const uint32_t v = i < total ? hist[i] : 0u;
+    const uint32_t v = i < nblocks ? row[i] : 0u;
     uint32_t inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -78,22 +81,23 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t* hist, int tot
     if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-      const uint32_t tv = warp_tot[lane];
+      const uint32_t tv = lane < 8 ? warp_tot[lane] : 0u;
       uint32_t ti = tv;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
+      for (int o = 1; o < 8; o <<= 1) {
         const uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
         if (lane >= o) ti += u;
       }
-      warp_tot[lane] = ti - tv;
-      if (lane == 31) warp_tot[32] = ti;
+      if (lane < 8) warp_tot[lane] = ti - tv;
+      if (lane == 7) warp_tot[8] = ti;
     }
     __syncthreads();
-    if (i < total) hist[i] = carry + warp_tot[warp] + inc - v;
+    if (i < nblocks) row[i] = carry + warp_tot[warp] + inc - v;
     __syncthreads();
-    if (threadIdx.x == 0) carry += warp_tot[32];
+    if (threadIdx.x == 0) carry += warp_tot[8];
     __syncthreads();
   }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
 }
 
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const SortParams p) {
@@ -136,7 +140,23 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const SortPa
   // cnt[d*W + w] = keys of this tile with a smaller digit, or the same digit in an earlier warp.  Turn it into the global
   // position: + (scanned global histogram of (d, tile)) - (keys of this tile with a smaller digit).
   __shared__ uint32_t dig_base[256];
-  if (threadIdx.x < 256) dig_base[threadIdx.x] = p.hist[(size_t)threadIdx.x * p.nblocks + blockIdx.x] - cnt[threadIdx.x * kSortWarps];
+  {
+    // exclusive scan of the 256 digit totals (first 8 warps), then: global start of digit d + keys of digit d in earlier
+    // tiles - keys of this tile with a smaller digit
+    const uint32_t tv = threadIdx.x < 256 ? p.totals[threadIdx.x] : 0u;
+    uint32_t inc = tv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (threadIdx.x < 256 && lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < warp && w < 8; ++w) before += warp_tot[w];
+    if (threadIdx.x < 256)
+      dig_base[threadIdx.x] = (before + inc - tv) + p.hist[(size_t)threadIdx.x * p.nblocks + blockIdx.x] - cnt[threadIdx.x * kSortWarps];
+  }
   __syncthreads();
   for (long long b0 = beg; b0 < end; b0 += 32) {
     const long long i = b0 + lane;
@@ -353,7 +373,7 @@ static ApLayout ap_layout(long long n, int n_thr, int max_class) {
   L.keyB = o; o = ap_align(o + nn * 8);
   L.idxA = o; o = ap_align(o + nn * 4);
   L.idxB = o; o = ap_align(o + nn * 4);
-  L.hist = o; o = ap_align(o + (size_t)256 * L.nblocks * 4);
+  L.hist = o; o = ap_align(o + (size_t)256 * L.nblocks * 4 + 1024);
   L.seg_start = o; o = ap_align(o + (size_t)(max_class + 2) * 4);
   L.seg_end = o; o = ap_align(o + (size_t)(max_class + 2) * 4);
   L.tp = o; o = ap_align(o + nn * n_thr * 4);
@@ -397,8 +417,9 @@ extern "C" int fvb_map_ap_f64(const float* d_dets, const uint8_t* d_correct, int
       SortParams sp;
       sp.src_key = key[cur]; sp.src_idx = idx[cur]; sp.dst_key = key[cur ^ 1]; sp.dst_idx = idx[cur ^ 1];
       sp.n = n_dets; sp.shift = shift; sp.nblocks = L.nblocks; sp.hist = (uint32_t*)(w + L.hist);
+      sp.totals = sp.hist + (size_t)256 * L.nblocks;
       sort_hist_kernel<<<L.nblocks, kSortThreads, 0, s>>>(sp);
-      sort_scan_kernel<<<1, 1024, 0, s>>>(sp.hist, 256 * L.nblocks);
+      sort_scan_kernel<<<256, 256, 0, s>>>(sp.hist, L.nblocks, sp.totals);
       sort_scatter_kernel<<<L.nblocks, kSortThreads, 0, s>>>(sp);
       count_launch(3);
       cur ^= 1;

@@ -134,3 +134,35 @@ def test_demo_loss_unaligned_grad_buffers(golden_demo_loss):
     lossf.backward_heads(heads, labels, cuda(g["ship_up"]), parts, mask, ctx=ctx, grads=grads)
     for i in range(3):
         gclose(grads[i], g["ship_grad%d" % i])
+
+
+def test_demo_loss_edge_cases(golden_demo_loss):
+    g = golden_demo_loss
+    anchors = [T(g["anchors%d" % i]) for i in range(3)]
+    heads = [cuda(g["head%d" % i]) for i in range(3)]
+    # no targets at all: the reference cannot run (IndexError); non-strict gives mean-of-empty NaNs for the target terms and the
+    # all-negative objectness mean
+    none = torch.zeros(0, 6, device="cuda")
+    with pytest.raises(IndexError):
+        ComputeLoss()(heads, none, _model(anchors))
+    lb, lc, lo = ComputeLoss(strict=False)(heads, none, _model(anchors))
+    assert torch.isnan(lb).all() and torch.isnan(lc).all()
+    want = sum(torch.nn.functional.binary_cross_entropy_with_logits(
+        h.view(h.size(0), 3, -1, h.size(2), h.size(3))[:, :, 4].double(), torch.zeros(h.size(0), 3, h.size(2), h.size(3), dtype=torch.float64, device="cuda"))
+        for h in heads)
+    close(lo, want.float().view(1))
+    # batch of one image, one target
+    one = [h[:1].contiguous() for h in heads]
+    lab = torch.tensor([[0, 1, 0.5, 0.5, 0.4, 0.3]], device="cuda")
+    hs = [h.cpu().clone().requires_grad_(True) for h in one]
+    wb, wc, wo = oracle.demo_loss.compute_loss(hs, lab.cpu(), anchors, "ship")
+    (wb + wc + wo).sum().backward()
+    dh = [h.clone().requires_grad_(True) for h in one]
+    gb, gc, go = ComputeLoss()(dh, lab, _model(anchors))
+    close(gb, wb); close(gc, wc); close(go, wo)
+    (gb + gc + go).sum().backward()
+    for a, b in zip(dh, hs):
+        gclose(a.grad, b.grad)
+    # CPU tensors are rejected (no fallback)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        ComputeLoss()([h.cpu() for h in heads], lab.cpu(), _model(anchors))

@@ -49,3 +49,15 @@ def test_postprocess_vs_oracle_608(form, fn):
         cat = cand[:, 5:].argmax(1).float()
         _, margin = nms_greedy(cand[:, :4] + cat[:, None] * 4096, cand[:, 4], args[1], return_iou_margin=True)
         assert margin < 1e-6, (s.shape, ws.shape, margin)
+
+
+def test_postprocess_nothing_survives(golden_postprocess):
+    g = golden_postprocess
+    heads = [cuda(g["head%d" % i]) for i in range(3)]
+    anchors = [cuda(g["anchors%d" % i]) for i in range(3)]
+    s, c, b = post_u(heads, SMALL.strides, anchors, 1.1, 0.4, 0.8, 3, 5, 72, 66)         # no objectness exceeds 1.1
+    assert s.shape == (0, 1) and c.shape == (0, 1) and b.shape == (0, 4)
+    s, c, b = post_ship(heads, SMALL.strides, anchors, 0.2, 0.4, 0.8, 3, 5, 4, 4)       # a 4x4 original image: every box <= 5 px
+    assert s.shape == (0, 1) and b.shape == (0, 4)
+    with pytest.raises(ValueError):
+        post_u([torch.cat([h, h]) for h in heads], SMALL.strides, anchors, 0.2, 0.4, 0.8, 3, 5, 72, 66)
