@@ -8,12 +8,13 @@
 //                      of yolov3_loss.py:63-64).  One 16-byte store per 4 floats; the objectness logits come from the compact
 //                      copy the forward saved (4 bytes per row) -- read strided from the heads they cost a 128-byte DRAM
 //                      fetch per row (ncu: 349 MB of reads next to 869 MB of writes at B=256).
-//   yolo_grad_match  : one warp per (level, target, anchor).  The LAST match of a cell (the one whose IoU the reference's
+//   yolo_grad_box / yolo_grad_rows : the matched rows.  The LAST match of a cell (the one whose IoU the reference's
 //                      index_put keeps, :61) owns the cell's row: it adds, in target order, the class-BCE, CIoU and
 //                      IoU-target gradients of every match that hit the cell (autograd's index backward scatter-adds
 //                      duplicates; index_put's backward hands the cell's objectness-target gradient to every duplicate)
-//                      and overwrites channel 4 with the gradient for target = IoU.  Single writer per row: no atomics,
-//                      bit-reproducible.
+//                      and overwrites channel 4 with the gradient for target = IoU.  Box math: one thread per (level,
+//                      target, anchor); class channels + row store: one warp per owned row.  Single writer per row: no
+//                      atomics on the gradients, bit-reproducible.
 //   iou_loss_grad / bce_grad : element-wise.
 #include "iou_grad.cuh"
 #include "loss_common.cuh"
@@ -146,142 +147,136 @@ __global__ void labels_grouped_kernel(const float* labels, int T, int* flags) {
   for (int t = threadIdx.x; t + 1 < T; t += blockDim.x)
     if ((int)labels[(size_t)t * 6] > (int)labels[(size_t)(t + 1) * 6]) bad = 1;
   __syncthreads();
-  if (threadIdx.x == 0) flags[0] = bad ? 0 : 1;
+  if (threadIdx.x == 0) {
+    flags[0] = bad ? 0 : 1;
+    flags[1] = 0;  // record counter of the matched-row pass
+  }
 }
 
-// Channels of one row held in registers: lane + 32*j, j < kRowRegs (K <= 128); wider rows fall back to read-modify-write.
-constexpr int kRowRegs = 4;
+// Matched rows, two phases.  The box / objectness gradient of a match is scalar work (reverse mode of CIoU + IoU): a warp
+// per match made 32 lanes repeat it (99 registers, 2 CTAs per SM, 45 us at B=256).  Phase 1 gives every (level, target,
+// anchor) ONE THREAD: ratio test, duplicate-cell scan, the four box-logit gradients summed over the cell's matches in target
+// order, the objectness gradient -- and appends a record for each cell it owns.  Phase 2 gives every record one WARP: the
+// class-BCE gradients of the row's channels (lanes over channels) and the coalesced row store.
+struct RowRecord {
+  unsigned long long row;  // offset of the row in floats inside its level tensor
+  int level, t, lo, dups;  // owner target, first target index of its image range to rescan, matches on the cell
+  int a, cls;
+  float g[4];
+  float conf_grad;
+  float pad;
+};
 
-__global__ void __launch_bounds__(kMatchThreads) yolo_grad_match_kernel(const GradParams p) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+struct MatchWs {
+  int* flags;            // [0] grouped, [1] record count
+  RowRecord* records;    // [L*T*A]
+};
+
+__device__ __forceinline__ bool same_cell(const TargetCell& x, const TargetCell& y) {
+  return y.match && y.gx == x.gx && y.gy == x.gy;
+}
+
+__global__ void __launch_bounds__(kMatchThreads) yolo_grad_box_kernel(const GradParams p, MatchWs ws) {
   const int TA = p.T * p.g.A;
-  const int l = blockIdx.y;
-  const int ta = blockIdx.x * (kMatchThreads / 32) + warp;
-  if (ta >= TA) return;
+  const int i = blockIdx.x * kMatchThreads + threadIdx.x;
+  if (i >= TA * p.g.L) return;
+  const int l = i / TA, ta = i - l * TA;
   const int t = ta / p.g.A, a = ta - t * p.g.A;
   const TargetCell c = target_cell(p.g, l, p.labels + (size_t)t * 6, a);
   if (!(c.match && c.b >= 0 && c.b < p.g.B)) return;
-  const bool grouped = p.flags[0] != 0;
-  const int K = p.g.K, C = K - 5;
-  const size_t rofs = cell_row(p.g, l, c.b, a, c.gy, c.gx) * K;
-  const float* row = p.g.head[l] + rofs;
-  float* grow = p.grad[l] + rofs;
-  const bool in_regs = K <= 32 * kRowRegs;
-
-  // the row is requested before the duplicate scans so that its DRAM latency overlaps them
-  float rv[kRowRegs];
-#pragma unroll
-  for (int j = 0; j < kRowRegs; ++j) rv[j] = (lane + 32 * j < K) ? __ldg(row + lane + 32 * j) : 0.0f;
-
-  // loser: a later target of the same image hits the same cell with the same anchor -> that warp owns the row
-  for (int t2b = t + 1; t2b < p.T; t2b += 32) {
-    const int t2 = t2b + lane;
-    bool hit = false;
-    int b2 = 0x7fffffff;
-    if (t2 < p.T) {
-      const float* lab2 = p.labels + (size_t)t2 * 6;
-      b2 = (int)lab2[0];
-      if (b2 == c.b) {
-        const TargetCell c2 = target_cell(p.g, l, lab2, a);
-        hit = c2.match && c2.gx == c.gx && c2.gy == c.gy;
-      }
+  const bool grouped = ws.flags[0] != 0;
+  // loser: a later target of the same image hits the same cell with the same anchor -> that thread owns the row
+  for (int t2 = t + 1; t2 < p.T; ++t2) {
+    const float* lab2 = p.labels + (size_t)t2 * 6;
+    const int b2 = (int)lab2[0];
+    if (b2 == c.b) {
+      if (same_cell(c, target_cell(p.g, l, lab2, a))) return;
+    } else if (grouped && b2 > c.b) {
+      break;
     }
-    if (__any_sync(0xffffffffu, hit)) return;
-    if (grouped && __all_sync(0xffffffffu, b2 > c.b)) break;
   }
-
+  const size_t rofs = cell_row(p.g, l, c.b, a, c.gy, c.gx) * p.g.K;
+  const float* row = p.g.head[l] + rofs;
+  const float r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2), r3 = __ldg(row + 3), r4 = __ldg(row + 4);
   const float gout = upstream(p);
   const double M = p.partials[l * 4 + 3];
   // (loss_box + loss_conf + loss_cls) * bs, ratios applied to the per-level means (yolov3_loss.py:52,58,66-72)
   const float w_box = (float)((double)gout * (double)p.batch_global * (double)p.r_box / M);
-  const float w_cls = (float)((double)gout * (double)p.batch_global * (double)p.r_cls / (M * (double)C));
   const float w_conf = conf_coef(p, l, gout);
-
-  const float first = rv[0];
-  const float r0 = __shfl_sync(0xffffffffu, first, 0), r1 = __shfl_sync(0xffffffffu, first, 1);
-  const float r2 = __shfl_sync(0xffffffffu, first, 2), r3 = __shfl_sync(0xffffffffu, first, 3);
-  const float r4 = __shfl_sync(0xffffffffu, first, 4);
   const float p4 = sigmoid_precise(r4);
   const float g_tgt = w_conf * bce_dt(p4);  // gradient reaching targets_conf[cell]; index_put backward gives it to every duplicate
-
-  // class-BCE factor of every channel this lane owns: w_cls * p(1-p) * d bce/dp for target 0 and for target 1
-  float acc[kRowRegs], g_neg[kRowRegs], g_pos[kRowRegs];
-#pragma unroll
-  for (int j = 0; j < kRowRegs; ++j) {
-    acc[j] = 0.0f;
-    const float pr = sigmoid_precise(rv[j]);
-    const float dsig = (1.0f - pr) * pr;
-    g_neg[j] = w_cls * (bce_dp(pr, 0.0f) * dsig);
-    g_pos[j] = w_cls * (bce_dp(pr, 1.0f) * dsig);
-  }
-  float conf_grad = 0.0f;
-
-  // contribution of one match (target t2, same level/anchor/cell) to the row gradient: this warp is the row's only
-  // writer after the dense pass (which left zeros there), so the sum is formed in registers, in target order
-  auto add_match = [&](int t2, bool self) {
-    const TargetCell m = self ? c : target_cell(p.g, l, p.labels + (size_t)t2 * 6, a);
-    const MatchRowGrad mg = match_row_grad(r0, r1, r2, r3, m, w_box, g_tgt);
-    if (self) conf_grad = w_conf * (bce_dp(p4, mg.iou) * ((1.0f - p4) * p4));
-    if (in_regs) {
-#pragma unroll
-      for (int j = 0; j < kRowRegs; ++j) {
-        const int ch = lane + 32 * j;
-        float add;
-        if (j == 0 && lane < 4) add = lane == 0 ? mg.g[0] : (lane == 1 ? mg.g[1] : (lane == 2 ? mg.g[2] : mg.g[3]));
-        else add = (ch - 5 == m.cls) ? g_pos[j] : g_neg[j];
-        acc[j] += add;
-      }
-    } else {
-      const float add = lane == 0 ? mg.g[0] : (lane == 1 ? mg.g[1] : (lane == 2 ? mg.g[2] : mg.g[3]));
-      if (lane < 4) grow[lane] += add;
-      for (int ch = lane; ch < K; ch += 32) {
-        if (ch < 5) continue;
-        const float pr = sigmoid_precise(row[ch]);
-        const float tg = (ch - 5 == m.cls) ? 1.0f : 0.0f;
-        grow[ch] += w_cls * (bce_dp(pr, tg) * ((1.0f - pr) * pr));
-      }
-    }
-  };
-
-  // earlier matches of the same cell, ascending target order
+  // first target of this image (grouped labels) -- earlier matches of the cell are added in ascending target order
   int lo = 0;
   if (grouped) {
-    for (int base = t - 1; base >= 0; base -= 32) {
-      const int t2 = base - lane;
-      const bool before = t2 >= 0 && (int)p.labels[(size_t)t2 * 6] < c.b;
-      const unsigned mk = __ballot_sync(0xffffffffu, before);
-      if (mk) {
-        lo = base - (__ffs(mk) - 1) + 1;
-        break;
-      }
-    }
+    lo = t;
+    while (lo > 0 && (int)p.labels[(size_t)(lo - 1) * 6] == c.b) --lo;
   }
-  for (int base = lo; base < t; base += 32) {
-    const int t2 = base + lane;
-    bool hit = false;
-    if (t2 < t) {
-      const float* lab2 = p.labels + (size_t)t2 * 6;
-      if ((int)lab2[0] == c.b) {
-        const TargetCell c2 = target_cell(p.g, l, lab2, a);
-        hit = c2.match && c2.gx == c.gx && c2.gy == c.gy;
-      }
-    }
-    unsigned mk = __ballot_sync(0xffffffffu, hit);
-    while (mk) {
-      const int i = __ffs(mk) - 1;
-      mk &= mk - 1;
-      add_match(base + i, false);
-    }
-  }
-  add_match(t, true);
-  if (in_regs) {
+  RowRecord r;
+  r.g[0] = r.g[1] = r.g[2] = r.g[3] = 0.0f;
+  r.dups = 0;
+  for (int t2 = lo; t2 < t; ++t2) {
+    const float* lab2 = p.labels + (size_t)t2 * 6;
+    if ((int)lab2[0] != c.b) continue;
+    const TargetCell m = target_cell(p.g, l, lab2, a);
+    if (!same_cell(c, m)) continue;
+    const MatchRowGrad mg = match_row_grad(r0, r1, r2, r3, m, w_box, g_tgt);
 #pragma unroll
-    for (int j = 0; j < kRowRegs; ++j) {
-      const int ch = lane + 32 * j;
-      if (ch < K) grow[ch] = ch == 4 ? conf_grad : acc[j];
+    for (int k = 0; k < 4; ++k) r.g[k] += mg.g[k];
+    r.dups += 1;
+  }
+  const MatchRowGrad mg = match_row_grad(r0, r1, r2, r3, c, w_box, g_tgt);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r.g[k] += mg.g[k];
+  r.dups += 1;
+  r.conf_grad = w_conf * (bce_dp(p4, mg.iou) * ((1.0f - p4) * p4));
+  r.row = (unsigned long long)rofs;
+  r.level = l;
+  r.t = t;
+  r.lo = lo;
+  r.a = a;
+  r.cls = c.cls;
+  r.pad = 0.0f;
+  ws.records[atomicAdd(&ws.flags[1], 1)] = r;  // record order is arbitrary; every record owns a distinct row
+}
+
+__global__ void __launch_bounds__(kMatchThreads) yolo_grad_rows_kernel(const GradParams p, MatchWs ws) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int count = ws.flags[1];
+  const int K = p.g.K, C = K - 5;
+  for (int ri = blockIdx.x * (kMatchThreads / 32) + warp; ri < count; ri += gridDim.x * (kMatchThreads / 32)) {
+    const RowRecord r = ws.records[ri];
+    const int l = r.level;
+    const float* row = p.g.head[l] + r.row;
+    float* grow = p.grad[l] + r.row;
+    const double M = p.partials[l * 4 + 3];
+    const float w_cls = (float)((double)upstream(p) * (double)p.batch_global * (double)p.r_cls / (M * (double)C));
+    TargetCell own;
+    if (r.dups > 1) own = target_cell(p.g, l, p.labels + (size_t)r.t * 6, r.a);
+    for (int ch = lane; ch < K; ch += 32) {
+      float gv;
+      if (ch < 4) gv = ch == 0 ? r.g[0] : (ch == 1 ? r.g[1] : (ch == 2 ? r.g[2] : r.g[3]));
+      else if (ch == 4) gv = r.conf_grad;
+      else {
+        const float pr = sigmoid_precise(__ldg(row + ch));
+        const float dsig = (1.0f - pr) * pr;
+        const float g_neg = w_cls * (bce_dp(pr, 0.0f) * dsig), g_pos = w_cls * (bce_dp(pr, 1.0f) * dsig);
+        if (r.dups == 1) {
+          gv = (ch - 5 == r.cls) ? g_pos : g_neg;
+        } else {
+          // several matches share the cell: their class terms add up in target order (torch's index backward)
+          gv = 0.0f;
+          const int b = (int)p.labels[(size_t)r.t * 6];
+          for (int t2 = r.lo; t2 <= r.t; ++t2) {
+            const float* lab2 = p.labels + (size_t)t2 * 6;
+            if ((int)lab2[0] != b) continue;
+            const TargetCell m = target_cell(p.g, l, lab2, r.a);
+            if (t2 != r.t && !same_cell(own, m)) continue;
+            gv += (ch - 5 == m.cls) ? g_pos : g_neg;
+          }
+        }
+      }
+      grow[ch] = gv;
     }
-  } else if (lane == 4) {
-    grow[4] = conf_grad;
   }
 }
 
@@ -379,7 +374,10 @@ __global__ void bce_grad_kernel(const float* pre, long long rows, int classes, c
 
 using namespace fvb;
 
-extern "C" size_t fvb_yolov3_loss_backward_workspace_bytes(void) { return 256; }
+extern "C" size_t fvb_yolov3_loss_backward_workspace_bytes(const fvb_yolo_geom* geom, int64_t num_labels) {
+  if (geom == nullptr || num_labels < 0) return 0;
+  return 256 + (size_t)geom->levels * (size_t)num_labels * (size_t)geom->anchors * sizeof(RowRecord) + 256;
+}
 
 extern "C" int fvb_yolov3_loss_backward_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
                                             int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
@@ -389,6 +387,7 @@ extern "C" int fvb_yolov3_loss_backward_f32(const fvb_yolo_geom* geom, const flo
   FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "yolov3_loss_backward: num_labels=%lld", (long long)num_labels);
   FVB_REQUIRE(num_labels == 0 || d_labels, "yolov3_loss_backward: labels NULL");
   FVB_REQUIRE(batch_global >= 1, "yolov3_loss_backward: batch_global=%lld", (long long)batch_global);
+  FVB_REQUIRE(((uintptr_t)d_ws & 255) == 0, "yolov3_loss_backward: workspace must be 256-byte aligned");
   GradParams p;
   int rc = make_geom(geom, d_heads, &p.g);
   if (rc != FVB_OK) return rc;
@@ -427,11 +426,15 @@ extern "C" int fvb_yolov3_loss_backward_f32(const fvb_yolo_geom* geom, const flo
   else yolo_grad_dense_kernel<false><<<(unsigned)ctas, kDenseThreads, 0, s>>>(p);
   count_launch();
   if (p.T > 0) {
-    labels_grouped_kernel<<<1, 1024, 0, s>>>(d_labels, p.T, (int*)d_ws);
-    const int wpb = kMatchThreads / 32;
-    dim3 grid((unsigned)(((long long)p.T * g.A + wpb - 1) / wpb), (unsigned)g.L);
-    yolo_grad_match_kernel<<<grid, kMatchThreads, 0, s>>>(p);
-    count_launch(2);
+    MatchWs mw;
+    mw.flags = (int*)d_ws;
+    mw.records = (RowRecord*)((unsigned char*)d_ws + 256);
+    labels_grouped_kernel<<<1, 1024, 0, s>>>(d_labels, p.T, mw.flags);   // also zeroes the record counter
+    const long long pairs = (long long)p.T * g.A * g.L;
+    yolo_grad_box_kernel<<<(unsigned)((pairs + kMatchThreads - 1) / kMatchThreads), kMatchThreads, 0, s>>>(p, mw);
+    const long long row_ctas = (pairs + kMatchThreads / 32 - 1) / (kMatchThreads / 32);
+    yolo_grad_rows_kernel<<<(unsigned)(row_ctas < 1184 ? row_ctas : 1184), kMatchThreads, 0, s>>>(p, mw);
+    count_launch(3);
   }
   return check_launch("yolov3_loss_backward");
 }

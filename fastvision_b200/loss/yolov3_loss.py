@@ -109,7 +109,7 @@ class Yolov3Loss(nn.Module):
         if grad_out is not None:
             grad_out = _lib.require_cuda(grad_out.detach().reshape(-1)[:1], "grad_out")
         lib = _lib.load()
-        ws = _lib.workspace(lib.fvb_yolov3_loss_backward_workspace_bytes(), dev, "yolov3_loss_bwd")
+        ws = _lib.workspace(lib.fvb_yolov3_loss_backward_workspace_bytes(ctx.geom, labels.size(0)), dev, "yolov3_loss_bwd")
         bg = int(batch_global) if batch_global else int(heads[0].size(0))
         with torch.cuda.device(dev):
             _lib.check(lib.fvb_yolov3_loss_backward_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), labels.size(0),

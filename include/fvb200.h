@@ -232,9 +232,9 @@ int fvb_yolov3_build_target_f32(const fvb_yolo_geom* geom, int level, const floa
  * backward do.  d_partials: the [L*4] f64 partials of the forward (M_l at [l*4+3]; all-reduced under data
  * parallelism, with batch_global the global batch).  d_saved_conf: the compact objectness logits written by
  * fvb_yolov3_loss_train_f32 over the same heads, or NULL.  d_grad_out: device scalar [1] (the upstream gradient) or NULL
- * for 1.  d_ws: fvb_yolov3_loss_backward_workspace_bytes() bytes.  Bit-reproducible (one writer per row, no atomics).
+ * for 1.  d_ws: fvb_yolov3_loss_backward_workspace_bytes(geom, num_labels) bytes, 256-byte aligned.  Bit-reproducible (one writer per row, no atomics).
  */
-size_t fvb_yolov3_loss_backward_workspace_bytes(void);
+size_t fvb_yolov3_loss_backward_workspace_bytes(const fvb_yolo_geom* geom, int64_t num_labels);
 int fvb_yolov3_loss_backward_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
                                  int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
                                  int64_t batch_global, const double* d_partials, const float* d_saved_conf,
