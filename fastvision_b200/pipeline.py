@@ -163,139 +163,6 @@ class ValStep:
         return [dets[i, :c] for i, c in enumerate(cnt)]
 
 
-class ChunkedValStep:
-    """The same step with the batch cut into ``chunks`` contiguous image chunks (one call, one batch, same outputs).
-
-    NMS is latency-bound (one CTA per image) and the loss kernels are tiny, so after a whole-batch decode the GPU idles
-    through an NMS tail of ~60-70 us.  Here chunk c's NMS + loss branches run on side streams while the main stream already
-    decodes chunk c+1 (the persistent decode kernel leaves shared memory for one NMS CTA per SM); only the LAST chunk's
-    tail is exposed, and with half the images it runs one NMS CTA per SM instead of two.  Nothing changes per image: the
-    decode, the NMS and the per-level loss partial sums (added over chunks, then combined with the global-batch
-    normalisers -- the same algebra the data-parallel path uses) are the reference's.  Capturable as one CUDA graph.
-    """
-
-    def __init__(self, anchors_per_level, strides, chunks=2, conf_thres=0.25, iou_thres=0.45, max_det=300,
-                 ratio_box=0.05, ratio_conf=1.0, ratio_cls=0.5, nms_flavour="lib", precise_decode=False,
-                 process_group=None, batch_global: Optional[int] = None):
-        self.anchors_per_level, self.strides = anchors_per_level, strides
-        self.chunks = int(chunks)
-        self.conf_thres, self.iou_thres, self.max_det = conf_thres, iou_thres, max_det
-        self.nms_flavour, self.precise = nms_flavour, precise_decode
-        self.loss_fn = Yolov3Loss(_ModelStub(anchors_per_level, strides), 0.5, ratio_box, ratio_conf, ratio_cls)
-        self.pg, self.batch_global = process_group, batch_global
-        self.ctx = None          # full-batch geometry (rows, k); chunk contexts own the decode side buffers
-        self.out = None
-        self.graph = None
-
-    def _distributed(self):
-        return self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                       and torch.distributed.get_world_size() > 1)
-
-    def _prepare(self, heads):
-        key = (tuple(tuple(h.shape) for h in heads), heads[0].device)
-        if self.ctx is not None and self._key == key:
-            return
-        self._key = key
-        self.ctx = DecodeContext(heads, self.anchors_per_level, self.strides)
-        ctx = self.ctx
-        dev, b, md = ctx.device, ctx.batch, self.max_det
-        n = max(1, min(self.chunks, b))
-        base, rem = divmod(b, n)
-        self.bounds = []
-        lo = 0
-        for c in range(n):
-            hi = lo + base + (1 if c < rem else 0)
-            self.bounds.append((lo, hi))
-            lo = hi
-        self.out = {
-            "results": torch.empty(b, ctx.rows, ctx.k, dtype=torch.float32, device=dev),
-            "boxes": torch.empty(b, md, 4, dtype=torch.float32, device=dev),
-            "scores": torch.empty(b, md, dtype=torch.float32, device=dev),
-            "cls": torch.empty(b, md, dtype=torch.int64, device=dev),
-            "cnt": torch.zeros(b, dtype=torch.int32, device=dev),
-            "rows": torch.empty(b, md, dtype=torch.int32, device=dev),
-            "loss": torch.empty(1, dtype=torch.float32, device=dev),
-            "partials": torch.empty(ctx.geom.levels, 4, dtype=torch.float64, device=dev),
-        }
-        self.cctx, self.cparts, self.coff = [], [], []
-        for lo, hi in self.bounds:
-            cc = DecodeContext([h[lo:hi] for h in heads], self.anchors_per_level, self.strides)
-            cc.bitmap(), cc.records(), cc.bce0(), cc.sched()
-            self.cctx.append(cc)
-            self.cparts.append(torch.empty(ctx.geom.levels, 4, dtype=torch.float64, device=dev))
-            self.coff.append(torch.tensor([float(lo), 0, 0, 0, 0, 0], dtype=torch.float32, device=dev))
-        self._nms_s = torch.cuda.Stream(device=dev)
-        self._loss_s = torch.cuda.Stream(device=dev)
-        self._ev_dec = [torch.cuda.Event() for _ in self.bounds]
-        self._ev_nms, self._ev_loss = torch.cuda.Event(), torch.cuda.Event()
-        self.graph = None
-
-    def _run(self, heads, labels):
-        o = self.out
-        main = torch.cuda.current_stream()
-        for c, (lo, hi) in enumerate(self.bounds):
-            cc = self.cctx[c]
-            hc = [h[lo:hi] for h in heads]
-            yolov3_decode(hc, self.anchors_per_level, self.strides, precise=self.precise, ctx=cc, out=o["results"][lo:hi],
-                          conf_thres=self.conf_thres, want_bce0=True)
-            self._ev_dec[c].record(main)
-            with torch.cuda.stream(self._loss_s):
-                self._loss_s.wait_event(self._ev_dec[c])
-                # labels keep their global image index; shifted by the chunk start, rows of other chunks fall outside
-                # [0, chunk batch) and are skipped by the kernels (the reference raises for such rows)
-                lc = labels if lo == 0 else torch.sub(labels, self.coff[c])
-                self.loss_fn(hc, lc, conf_bce0=cc.bce0(), ctx=cc, out=o["loss"], partials=self.cparts[c])
-            with torch.cuda.stream(self._nms_s):
-                self._nms_s.wait_event(self._ev_dec[c])
-                non_max_suppression_batched(o["results"][lo:hi], self.conf_thres, self.iou_thres, self.max_det, self.nms_flavour,
-                                            cand_bitmap=cc.bitmap(), cand_records=cc.records(), clear_bitmap=True,
-                                            out=(o["boxes"][lo:hi], o["scores"][lo:hi], o["cls"][lo:hi], o["cnt"][lo:hi],
-                                                 o["rows"][lo:hi]))
-        with torch.cuda.stream(self._loss_s):
-            torch.add(self.cparts[0], self.cparts[1], out=o["partials"]) if len(self.cparts) > 1 else o["partials"].copy_(self.cparts[0])
-            for extra in self.cparts[2:]:
-                o["partials"].add_(extra)
-            bg = self.ctx.batch
-            if self._distributed():
-                torch.distributed.all_reduce(o["partials"], group=self.pg)
-                bg = self.batch_global or self.ctx.batch * torch.distributed.get_world_size(self.pg)
-            self.loss_fn.combine(o["partials"], bg, ctx=self.cctx[0], out=o["loss"])
-            self._ev_loss.record(self._loss_s)
-        self._ev_nms.record(self._nms_s)
-        main.wait_event(self._ev_nms)
-        main.wait_event(self._ev_loss)
-        return o
-
-    def __call__(self, head_out: List[torch.Tensor], labels: torch.Tensor):
-        heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
-        labels = _lib.require_cuda(labels, "labels").view(-1, 6)
-        self._prepare(heads)
-        return self._run(heads, labels)
-
-    def capture(self, head_out, labels):
-        """Capture the whole step for these (static) input tensors into one CUDA graph; returns the replay callable.
-        Under torch.distributed the NCCL all-reduce stays outside any graph: the step is launched eagerly."""
-        heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
-        labels = _lib.require_cuda(labels, "labels").view(-1, 6)
-        self._prepare(heads)
-        if self._distributed():
-            return lambda: self._run(heads, labels)
-        warm = torch.cuda.Stream(device=self.ctx.device)
-        warm.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(warm):
-            for _ in range(2):
-                self._run(heads, labels)
-        torch.cuda.current_stream().wait_stream(warm)
-        torch.cuda.synchronize(self.ctx.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._run(heads, labels)
-        self.graph = g
-        return g.replay
-
-    detections = ValStep.detections
-
-
 class ValPipeline:
     """Software-pipelined validation loop: the NMS + loss tail of batch i overlaps the decode of batch i+1.
 

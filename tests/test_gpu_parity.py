@@ -481,35 +481,3 @@ def test_decode_nchw_heads(cfg, batch):
     got_yxa = yolov3_decode([h.cuda() for h in nchw], anc, st, layout="nchw", row_order="yxa")
     close(got_yxa, oracle.decode.decode_demo_nchw(nchw, anc_feat, st, order="yxa"))
 
-
-@pytest.mark.parametrize("chunks", [2, 3])
-def test_chunked_val_step_equals_plain_step(chunks):
-    """ChunkedValStep (NMS/loss of chunk c under the decode of chunk c+1) returns what ValStep returns: decoded rows and
-    detections bit for bit, the loss to fp64-partial-sum reordering."""
-    from fastvision_b200.pipeline import ChunkedValStep
-    cfg, batch = synth.COCO416, 7                                # uneven chunks
-    g = synth.make_generator(1)
-    labels = synth.make_labels(cfg, batch, g)
-    heads = synth.make_heads(cfg, batch, labels, g)
-    dh, dl = [h.cuda() for h in heads], labels.cuda()
-    plain = ValStep(cfg.anchors_levels(), cfg.strides)
-    want = {k: v.clone() for k, v in plain(dh, dl).items()}
-    step = ChunkedValStep(cfg.anchors_levels(), cfg.strides, chunks=chunks)
-    out = step(dh, dl)
-    torch.cuda.synchronize()
-    assert torch.equal(out["results"], want["results"]) and torch.equal(out["cnt"], want["cnt"])
-    for i in range(batch):
-        k = int(want["cnt"][i])
-        for key in ("boxes", "scores", "cls", "rows"):
-            assert torch.equal(out[key][i, :k], want[key][i, :k]), (key, i)
-    close(out["loss"], want["loss"], rtol=1e-6)
-    close(out["partials"], want["partials"], rtol=1e-9)
-    close(out["loss"], ol.yolov3_loss(heads, labels, cfg.anchors_levels(), cfg.strides))
-    replay = step.capture(dh, dl)
-    snap = {k: v.clone() for k, v in out.items()}
-    for v in out.values():
-        v.zero_()
-    replay()
-    torch.cuda.synchronize()
-    for key in ("results", "loss", "cnt", "partials"):
-        assert torch.equal(out[key], snap[key]), key
