@@ -83,6 +83,8 @@ _SIGS = {
                                                  C.c_float, _P]),
     "fvb_map_ap_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "fvb_map_ap_f64": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "fvb_kmeans_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "fvb_kmeans_step_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
 }
 
 EXPORTS = tuple(_SIGS)

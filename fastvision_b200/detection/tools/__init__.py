@@ -6,6 +6,7 @@ from .iou import (cal_iou, cal_iou_batch, xyxy_iou, xywh_iou, wh_iou, xyxy_iou_b
 from .nms import (non_max_suppression, non_max_suppression_batched, non_max_suppression_demo, non_max_suppression_batch,
                   non_max_suppression_frcnn, nms)
 from .rpn import filter_proposals, filter_proposals_batched, make_anchors_xywh, get_base_anchor
+from .anchor import KMeans, AnchorGenerator
 
 __all__ = [
     "xywh2xyxy", "xyxy2xywh", "xyxy2xywhn", "grid", "offset",
@@ -14,4 +15,5 @@ __all__ = [
     "non_max_suppression", "non_max_suppression_batched", "non_max_suppression_demo", "non_max_suppression_batch",
     "non_max_suppression_frcnn", "nms",
     "filter_proposals", "filter_proposals_batched", "make_anchors_xywh", "get_base_anchor",
+    "KMeans", "AnchorGenerator",
 ]

@@ -296,6 +296,15 @@ int fvb_map_ap_f64(const float* d_dets, const uint8_t* d_correct, int64_t n_dets
                    int64_t n_targets, int n_thr, int max_class, double* d_ap, int32_t* d_pos_count, void* d_ws,
                    void* stream);
 
+/* ---- anchor k-means --------------------------------------------------------------------------------------
+ * One iteration of KMeans._fit, detection/tools/ANCHOR.py:33-46: d_categories[i] = 1 + argmin_c (1 - wh_iou(sample_i,
+ * centre_c)) (first minimum; wh_iou_batch numpy branch, detection/tools/IOU.py:166-175), d_new_centers[c] = mean of the
+ * samples assigned to c, or the old centre for an empty cluster.  d_samples [n,2], d_centers / d_new_centers [k,2] (k <= 64,
+ * must not alias).  Means are formed from fp64 sums (the reference: np.mean of float32). */
+size_t fvb_kmeans_workspace_bytes(int k);
+int fvb_kmeans_step_f32(const float* d_samples, int64_t n, const float* d_centers, int k, float eps, int64_t* d_categories,
+                        float* d_new_centers, void* d_ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,5 +22,5 @@ torchvision 0.11.2+cu113, source not in the reference tree): ``oracle.nms.nms_gr
 restates its published algorithm and is pinned against the torchvision 0.26.0 CPU op that
 ships in this image (golden vectors + a live check when torchvision imports).
 """
-from . import boxes, iou, decode, nms, loss, rpn, grad, demo_loss, postprocess  # noqa: F401
+from . import boxes, iou, decode, nms, loss, rpn, grad, demo_loss, postprocess, anchor  # noqa: F401
 from . import map as map_  # noqa: F401

@@ -428,6 +428,30 @@ def gold_postprocess(ns):
     np.savez_compressed(os.path.join(OUT, "postprocess.npz"), **out)
 
 
+def anchor_samples(n, seed):
+    """Normalised (w, h) samples around 9 COCO-like anchor shapes."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.tensor(synth.COCO416.anchors_px, dtype=torch.float32) / 416.0
+    pick = torch.randint(0, 9, (n,), generator=g)
+    wh = base[pick] * torch.exp(torch.randn(n, 2, generator=g) * 0.25)
+    return wh.clamp(0.005, 1.0).numpy().astype(np.float32)
+
+
+def gold_anchor(ns):
+    """KMeans of detection/tools/ANCHOR.py (seeded numpy RNG) -> tests/golden/anchor_kmeans.npz."""
+    import importlib
+    A = importlib.import_module("fastvision.detection.tools.ANCHOR")
+    out = {}
+    for tag, (n, k, iters, seed) in {"a": (600, 9, 25, 3), "b": (50, 12, 8, 4)}.items():
+        xs = anchor_samples(n, seed)
+        out[tag + "_samples"] = xs.copy()
+        out[tag + "_cfg"] = np.array([k, iters, seed], dtype=np.int64)
+        np.random.seed(seed)
+        centers, cats = A.KMeans(xs=xs.copy(), k=k).fit(iters=iters)
+        out[tag + "_centers"], out[tag + "_categories"] = np.asarray(centers), np.asarray(cats)
+    np.savez_compressed(os.path.join(OUT, "anchor_kmeans.npz"), **out)
+
+
 def main():
     if "--only-frcnn-nms" in sys.argv:
         torch.set_num_threads(1)
@@ -440,6 +464,9 @@ def main():
     if "--only-postprocess" in sys.argv:
         torch.set_num_threads(1)
         gold_postprocess(ref_shim.load())
+        return
+    if "--only-anchor" in sys.argv:
+        gold_anchor(ref_shim.load())
         return
     if "--only-grads" in sys.argv:
         torch.set_num_threads(1)
@@ -457,6 +484,7 @@ def main():
     gold_grads(ns)
     gold_demo_loss(ns)
     gold_postprocess(ns)
+    gold_anchor(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -62,3 +62,8 @@ def golden_demo_loss():
 @pytest.fixture(scope="session")
 def golden_postprocess():
     return load_golden("postprocess.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_anchor():
+    return load_golden("anchor_kmeans.npz")

@@ -278,3 +278,13 @@ def test_demo_postprocess(golden_postprocess, demo, form):
     s, c, b, _ = oracle.postprocess.post_process(heads, SMALL.strides, anchors, ct, it, rr, int(pl), int(pt), int(ow), int(oh), form)
     CLOSE(s, g[demo + "_scores"]); CLOSE(b, g[demo + "_boxes"])
     assert np.array_equal(c.numpy(), g[demo + "_cats"])
+
+
+# ---- anchor k-means (detection/tools/ANCHOR.py) ----------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_anchor_kmeans(golden_anchor, tag):
+    g = golden_anchor
+    k, iters, seed = (int(v) for v in g[tag + "_cfg"])
+    np.random.seed(seed)
+    centers, cats = oracle.anchor.KMeans(g[tag + "_samples"].copy(), k).fit(iters)
+    assert np.array_equal(np.asarray(centers), g[tag + "_centers"]) and np.array_equal(cats, g[tag + "_categories"])
