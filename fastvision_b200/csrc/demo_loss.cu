@@ -79,10 +79,10 @@ struct DemoParams {
   double* tgt_ws;  // [L][tgt_blocks][4]
   double* cell_ws; // [cell_ctas][2]
   int tgt_blocks;
-  int cell_cta_begin[FVB_MAX_LEVELS + 1];
-  int cell_chunks[FVB_MAX_LEVELS];   // CTAs per image on each level
+  int cell_cta_begin[FVB_MAX_LEVELS + 1];  // first demo_cells CTA of each level (B CTAs per level)
+  int cell_chunks[FVB_MAX_LEVELS];
   long long mask_off[FVB_MAX_LEVELS];
-  signed char* mask;  // optional [l][b][a][cell]
+  signed char* mask;  // [l][b][a][cell]: the caller's buffer or a workspace region
   double* partials;   // [L][kDemoParts]
   float* out;         // [3]
 };
@@ -221,117 +221,123 @@ __device__ __forceinline__ float bce_logits_stream(float x, float t) {
   return (1.0f - t) * x - (fminf(x, 0.0f) - log1pf(e));
 }
 
+// exact cell -> (row, column) without an integer division (cell < 2^22, W <= 2^11 by the geometry limits)
+__device__ __forceinline__ void cell_yx(int cell, int W, float inv_w, int* gy, int* gx) {
+  int y = __float2int_rz((float)cell * inv_w);
+  int x = cell - y * W;
+  if (x >= W) {
+    x -= W;
+    ++y;
+  } else if (x < 0) {
+    x += W;
+    --y;
+  }
+  *gy = y;
+  *gx = x;
+}
+
+// One CTA = one (level, image, anchor): it stages the image's targets ONCE and then walks the anchor's plane in chunks of
+// kCellChunk cells (per-CTA fixed costs -- the dependent img_off -> img_list -> labels -> key loads, the barriers, the block
+// reduction -- were paid per 1024 boxes before and capped the kernel at ~35 % active warps).  Inside a plane a = const and
+// cells are consecutive: no per-box divisions.
 __global__ void __launch_bounds__(kCellThreads) demo_cells_kernel(const DemoParams p) {
   __shared__ Box s_box[kStage];
   __shared__ int s_key[kStage];
-  __shared__ float s_aw[FVB_MAX_ANCHORS], s_ah[FVB_MAX_ANCHORS];
   __shared__ double scratch[32];
-  int l = 0;
-#pragma unroll
-  for (int i = 1; i < FVB_MAX_LEVELS; ++i)
-    if (i < p.g.L && (int)blockIdx.x >= p.cell_cta_begin[i]) l = i;
-  const int id = (int)blockIdx.x - p.cell_cta_begin[l];
-  const int b = id / p.cell_chunks[l], chunk = id - b * p.cell_chunks[l];
-  const int HW = p.g.HW[l], W = p.g.W[l], K = p.g.K;
-  const int boxes = p.g.A * HW;
-  const float* __restrict__ head = p.g.head[l] + (size_t)b * p.g.A * K * HW;
-  if ((int)threadIdx.x < p.g.A) {
-    s_aw[threadIdx.x] = p.g.aw[l][threadIdx.x] / p.g.stride[l];
-    s_ah[threadIdx.x] = p.g.ah[l][threadIdx.x] / p.g.stride[l];
-  }
-
-  // this thread's boxes: objectness logit now; the box itself only if some target can reach IoU > 0.5 with it
-  int ja[kCellBoxes], jcell[kCellBoxes];
-  float conf[kCellBoxes], cgx[kCellBoxes], cgy[kCellBoxes];
-  bool pos[kCellBoxes], ign[kCellBoxes], cand[kCellBoxes];
-#pragma unroll
-  for (int q = 0; q < kCellBoxes; ++q) {
-    const int j = chunk * kCellChunk + q * kCellThreads + threadIdx.x;
-    pos[q] = ign[q] = cand[q] = false;
-    conf[q] = 0.0f;
-    ja[q] = jcell[q] = 0;
-    cgx[q] = cgy[q] = 0.0f;
-    if (j < boxes) {
-      const int a = j / HW, cell = j - a * HW;
-      const int gy = cell / W;
-      ja[q] = a;
-      jcell[q] = cell;
-      cgx[q] = (float)(cell - gy * W);
-      cgy[q] = (float)gy;
-      conf[q] = __ldg(head + ((size_t)a * K + 4) * HW + cell);
-    }
-  }
-  // targets of image b, kStage at a time
+  __shared__ int s_cnt[kCellThreads / 32];
+  // big levels first: CTA x -> level L-1-(x / (B*A)) keeps the long CTAs at the front of the schedule
+  const int HW0 = p.g.A * p.g.B;
+  const int l = p.g.L - 1 - (int)blockIdx.x / HW0;
+  const int rem = (int)blockIdx.x % HW0;
+  const int b = rem / p.g.A, a = rem - b * p.g.A;
+  const int HW = p.g.HW[l], W = p.g.W[l], K = p.g.K, A = p.g.A;
+  const float inv_w = 1.0f / (float)W;
+  const float* __restrict__ img = p.g.head[l] + (size_t)b * A * K * HW;
+  const int chunks = (HW + kCellChunk - 1) / kCellChunk;
   const int beg = p.img_off[b], end = p.img_off[b + 1];
-  const int key_base = b * p.g.A * HW;
-  for (int s0 = beg; s0 < end; s0 += kStage) {
-    const int ns = min(kStage, end - s0);
+  const int key_base = b * A * HW;
+  signed char* mimg = p.mask + p.mask_off[l] + (long long)b * A * HW;  // caller's mask, or a workspace copy
+  float sum = 0.0f;  // a few dozen terms per thread at most: fp32 here, fp64 across threads
+  int cnt = 0;
+
+  for (int s0 = beg; s0 < max(end, beg + 1); s0 += kStage) {  // one round for <= kStage targets (also for none)
+    const int ns = max(0, min(kStage, end - s0));
+    const bool first_round = s0 == beg, last_round = s0 + kStage >= end;
     __syncthreads();
     if ((int)threadIdx.x < ns) {
       const int t = p.img_list[s0 + threadIdx.x];
       const DemoTarget d = demo_target(p.g, l, p.labels + (size_t)t * 6);
       s_box[threadIdx.x] = xywh_to_xyxy(d.x, d.y, d.w, d.h);
       const int key = p.key[(size_t)l * p.T + t];
-      s_key[threadIdx.x] = key >= 0 ? key - key_base : -1;
+      s_key[threadIdx.x] = key >= 0 ? key - key_base : -1;  // a*HW + cell inside this image
     }
     __syncthreads();
-    // IoU > 0.5 needs the intersection to cover more than half of each box, hence more than half of the predicted box's
-    // width and height: its centre (sigmoid + cell, inside [g, g+1]) must lie inside the target box.  Cells that no target
-    // box touches skip the four box planes and all transcendental math (exact: the test is conservative).
+    {
+      const float* __restrict__ plane = img + (size_t)a * K * HW;  // channel 0 of this anchor
+      const float aw = p.g.aw[l][a] / p.g.stride[l], ah = p.g.ah[l][a] / p.g.stride[l];
+      for (int chunk = 0; chunk < chunks; ++chunk) {
+        const int cell0 = chunk * kCellChunk;
+        // rows touched by this chunk: a target whose box misses them cannot make one of its cells a candidate
+        const float row_lo = (float)(cell0 / W), row_hi = (float)(min(cell0 + kCellChunk, HW) - 1) / (float)W + 1.0f;
 #pragma unroll
-    for (int q = 0; q < kCellBoxes; ++q) {
-      const int j = chunk * kCellChunk + q * kCellThreads + threadIdx.x;
-      bool c = false;
-      for (int i = 0; i < ns; ++i) {
-        const Box tb = s_box[i];
-        c = c || (cgx[q] <= tb.x2 && cgx[q] + 1.0f >= tb.x1 && cgy[q] <= tb.y2 && cgy[q] + 1.0f >= tb.y1);
-        pos[q] = pos[q] || (s_key[i] == j);
-      }
-      cand[q] = c && j < boxes && !ign[q];
-    }
-#pragma unroll
-    for (int q = 0; q < kCellBoxes; ++q) {
-      if (!cand[q]) continue;
-      const float* q0 = head + (size_t)ja[q] * K * HW + jcell[q];
-      const float t0 = __ldg(q0), t1 = __ldg(q0 + HW), t2 = __ldg(q0 + 2 * (size_t)HW), t3 = __ldg(q0 + 3 * (size_t)HW);
-      // lossv3.py:65-69
-      const Box pb = xywh_to_xyxy(sigmoid_precise(t0) + cgx[q], sigmoid_precise(t1) + cgy[q], expf(t2) * s_aw[ja[q]],
-                                  expf(t3) * s_ah[ja[q]]);
-      const float area_p = (pb.x2 - pb.x1) * (pb.y2 - pb.y1);
-      bool hit = false;
-      for (int i = 0; i < ns && !hit; ++i) {
-        const Box tb = s_box[i];
-        const float inter = inter_area(pb, tb);
-        if (inter > 0.0f) {
-          // xywh_iou_batch (lossv3.py:106): inter / (area_p + area_t - inter + eps) > 0.5 (:110); the division is only
-          // evaluated inside a guard band around the threshold
-          const float uni = ((area_p + (tb.x2 - tb.x1) * (tb.y2 - tb.y1)) - inter) + 1e-7f;
-          if (inter > 0.5000005f * uni) hit = true;
-          else if (inter >= 0.4999995f * uni) hit = inter / uni > 0.5f;
+        for (int q = 0; q < kCellBoxes; ++q) {
+          const int cell = cell0 + q * kCellThreads + threadIdx.x;
+          if (cell >= HW) continue;
+          const float conf = __ldg(plane + 4 * (size_t)HW + cell);
+          int gy, gx;
+          cell_yx(cell, W, inv_w, &gy, &gx);
+          const float cgx = (float)gx, cgy = (float)gy;
+          // mask state carried across target rounds (only when an image has more than kStage targets)
+          signed char m = first_round ? (signed char)0 : mimg[a * HW + cell];
+          bool pos = m > 0, ign = m < 0, c = false;
+          const int jkey = a * HW + cell;
+          // IoU > 0.5 needs the intersection to cover more than half of each box, hence more than half of the predicted
+          // box's width and height: its centre (sigmoid + cell, inside [g, g+1]) must lie inside the target box.  Cells
+          // that no target box touches skip the four box planes and all transcendental math (exact: conservative test).
+          for (int i = 0; i < ns; ++i) {
+            pos = pos || (s_key[i] == jkey);
+            const Box tb = s_box[i];
+            if (tb.y2 < row_lo || tb.y1 > row_hi) continue;  // uniform over the CTA
+            c = c || (cgx <= tb.x2 && cgx + 1.0f >= tb.x1 && cgy <= tb.y2 && cgy + 1.0f >= tb.y1);
+          }
+          if (c && !ign) {
+            const float* q0 = plane + cell;
+            const float t0 = __ldg(q0), t1 = __ldg(q0 + HW), t2 = __ldg(q0 + 2 * (size_t)HW), t3 = __ldg(q0 + 3 * (size_t)HW);
+            // lossv3.py:65-69
+            const Box pb = xywh_to_xyxy(sigmoid_precise(t0) + cgx, sigmoid_precise(t1) + cgy, expf(t2) * aw, expf(t3) * ah);
+            const float area_p = (pb.x2 - pb.x1) * (pb.y2 - pb.y1);
+            for (int i = 0; i < ns && !ign; ++i) {
+              const Box tb = s_box[i];
+              const float inter = inter_area(pb, tb);
+              if (inter > 0.0f) {
+                // xywh_iou_batch (lossv3.py:106): inter / (area_p + area_t - inter + eps) > 0.5 (:110); the division is
+                // only evaluated inside a guard band around the threshold
+                const float uni = ((area_p + (tb.x2 - tb.x1) * (tb.y2 - tb.y1)) - inter) + 1e-7f;
+                if (inter > 0.5000005f * uni) ign = true;
+                else if (inter >= 0.4999995f * uni) ign = inter / uni > 0.5f;
+              }
+            }
+          }
+          // mask: -1 ignore (max IoU > 0.5, lossv3.py:110), then positives overwrite with 1 (:115)
+          m = pos ? 1 : (ign ? -1 : 0);
+          mimg[a * HW + cell] = m;
+          if (last_round && m >= 0) {
+            sum += bce_logits_stream(conf, (float)m);  // :118-120
+            cnt += 1;
+          }
         }
       }
-      ign[q] = hit;
     }
   }
-  double sum = 0.0, cnt = 0.0;
-#pragma unroll
-  for (int q = 0; q < kCellBoxes; ++q) {
-    const int j = chunk * kCellChunk + q * kCellThreads + threadIdx.x;
-    if (j < boxes) {
-      // mask: -1 ignore (max IoU > 0.5, lossv3.py:110), then positives overwrite with 1 (:115)
-      const signed char m = pos[q] ? 1 : (ign[q] ? -1 : 0);
-      if (p.mask) p.mask[p.mask_off[l] + (long long)b * boxes + j] = m;
-      if (m >= 0) {
-        sum += (double)bce_logits_stream(conf[q], (float)m);  // :118-120
-        cnt += 1.0;
-      }
-    }
-  }
-  sum = block_sum(sum, scratch);
-  cnt = block_sum(cnt, scratch);
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  const double total = block_sum((double)sum, scratch);  // syncs: s_cnt is complete too
   if (threadIdx.x == 0) {
-    p.cell_ws[(size_t)blockIdx.x * 2] = sum;
-    p.cell_ws[(size_t)blockIdx.x * 2 + 1] = cnt;
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < kCellThreads / 32; ++w) c += s_cnt[w];
+    p.cell_ws[(size_t)blockIdx.x * 2] = total;
+    p.cell_ws[(size_t)blockIdx.x * 2 + 1] = (double)c;
   }
 }
 
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(1024) demo_finalize_kernel(const DemoParams p)
     double cs = 0.0, cn = 0.0;
     {
       const double2* cw = reinterpret_cast<const double2*>(p.cell_ws);
-      const int e = p.cell_cta_begin[l + 1], st = blockDim.x;
+      const int e = p.cell_cta_begin[l] + p.g.B * p.g.A, st = blockDim.x;
       int i = p.cell_cta_begin[l] + threadIdx.x;
       for (; i + 3 * st < e; i += 4 * st) {  // four independent 16-byte loads in flight
         const double2 a = cw[i], b2 = cw[i + st], c2 = cw[i + 2 * st], d2 = cw[i + 3 * st];
@@ -606,7 +612,7 @@ __global__ void __launch_bounds__(kTgtThreads) demo_grad_targets_kernel(const De
 static size_t align_up_(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct DemoLayout {
-  size_t key, img_off, img_cur, img_list, tgt_ws, cell_ws, total;
+  size_t key, img_off, img_cur, img_list, tgt_ws, cell_ws, mask, total;
   int tgt_blocks, cell_ctas;
 };
 
@@ -619,19 +625,16 @@ static DemoLayout demo_layout(const Geom& g, long long T, DemoParams* p) {
   L.img_list = o; o = align_up_(o + (size_t)(T > 0 ? T : 1) * 4, 256);
   L.tgt_blocks = (int)((T + kTgtThreads / 32 - 1) / (kTgtThreads / 32));
   L.tgt_ws = o;   o = align_up_(o + (size_t)g.L * (size_t)(L.tgt_blocks > 0 ? L.tgt_blocks : 1) * 4 * 8, 256);
-  int ctas = 0;
-  for (int l = 0; l < g.L; ++l) {
-    const int chunks = (g.A * g.HW[l] + kCellChunk - 1) / kCellChunk;
-    if (p) {
-      p->cell_cta_begin[l] = ctas;
-      p->cell_chunks[l] = chunks;
-    }
-    ctas += chunks * g.B;
-  }
+  // one demo_cells CTA per (level, image, anchor); CTA x handles level L-1-x/(B*A): level l owns B*A consecutive CTAs
+  const int ctas = g.L * g.B * g.A;
   if (p)
-    for (int l = g.L; l <= FVB_MAX_LEVELS; ++l) p->cell_cta_begin[l] = ctas;
+    for (int l = 0; l < FVB_MAX_LEVELS; ++l) {
+      p->cell_cta_begin[l] = l < g.L ? (g.L - 1 - l) * g.B * g.A : 0;
+      p->cell_chunks[l] = 1;
+    }
   L.cell_ctas = ctas;
   L.cell_ws = o;  o = align_up_(o + (size_t)(ctas > 0 ? ctas : 1) * 16, 256);
+  L.mask = o;     o = align_up_(o + (size_t)g.B * g.row_off[g.L], 256);  // used when the caller does not ask for the mask
   L.total = o + 256;
   return L;
 }
@@ -687,7 +690,7 @@ extern "C" int fvb_demo_loss_f32(const fvb_yolo_geom* geom, const float* const* 
   p.tgt_ws = (double*)(w + L.tgt_ws);
   p.cell_ws = (double*)(w + L.cell_ws);
   p.tgt_blocks = L.tgt_blocks;
-  p.mask = (signed char*)d_mask;
+  p.mask = d_mask ? (signed char*)d_mask : (signed char*)(w + L.mask);
   for (int l = 0; l < FVB_MAX_LEVELS; ++l) p.mask_off[l] = l < p.g.L ? (long long)p.g.B * p.g.row_off[l] : 0;
   p.partials = d_partials;
   p.out = d_out;
