@@ -6,7 +6,8 @@
 // IoU > 0.5 (the reference's per-image Python loop over xywh_iou_batch([A*H*W,4],[T_i,4]), lossv3.py:102-113) and 0
 // elsewhere; every term is a mean (BCE-with-logits / MSE / 1-CIoU).
 //
-//   demo_prep     : keys (cell ids) of every (level, target) + per-image target lists (counting sort, one CTA)
+//   demo_prep     : per-image target lists (identity + boundaries for grouped labels, else counting sort, one CTA);
+//   demo_keys     : keys (cell ids) of every (level, target)
 //   demo_targets  : one warp per (level, target): gather the matched row from the NCHW planes, box / xy-wh and class terms
 //   demo_cells    : HBM-bound stream over the 5 head planes of every anchor: decode the box, max pairwise IoU against the
 //                   image's targets staged in shared memory, ignore / positive / negative, objectness BCE; optionally
@@ -87,23 +88,41 @@ struct DemoParams {
   float* out;         // [3]
 };
 
+// Per-image target lists.  Labels grouped by image (collate_fn order, the normal case): the list is the identity and the
+// offsets are the positions where the image index changes -- one pass, no atomics.  Otherwise: counting sort with atomic
+// cursors, then every (short) list is sorted ascending so that the backward adds duplicates in target order.
 __global__ void __launch_bounds__(1024) demo_prep_kernel(const DemoParams p) {
   __shared__ int warp_tot[33];
   __shared__ int carry;
+  __shared__ int bad;
   const int B = p.g.B, T = p.T;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i <= B; i += blockDim.x) p.img_off[i] = 0;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) p.img_cur[i] = 0;
-  if (threadIdx.x == 0) carry = 0;
+  if (threadIdx.x == 0) {
+    carry = 0;
+    bad = 0;
+  }
   __syncthreads();
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const float* lab = p.labels + (size_t)t * 6;
-    const int b = (int)lab[0];
-    if (b >= 0 && b < B) atomicAdd(&p.img_off[b + 1], 1);
-    for (int l = 0; l < p.g.L; ++l) {
-      const DemoTarget d = demo_target(p.g, l, lab);
-      p.key[(size_t)l * T + t] = d.ok ? (d.b * p.g.A + d.a) * p.g.HW[l] + d.gy * p.g.W[l] + d.gx : -1;
+    const int b = (int)p.labels[(size_t)t * 6];
+    const int bp = t > 0 ? (int)p.labels[(size_t)(t - 1) * 6] : -1;
+    if (b < bp || b < 0 || b >= B) bad = 1;  // out of order, or an image index outside the batch
+  }
+  __syncthreads();
+  if (!bad) {
+    for (int t = threadIdx.x; t <= T; t += blockDim.x) {
+      const int b = t < T ? (int)p.labels[(size_t)t * 6] : B;
+      const int bp = t > 0 ? (int)p.labels[(size_t)(t - 1) * 6] : -1;
+      for (int i = bp + 1; i <= b; ++i) p.img_off[i] = t;  // images bp+1 .. b start at t (empty ones too)
+      if (t < T) p.img_list[t] = t;
     }
+    return;
+  }
+  for (int i = threadIdx.x; i <= B; i += blockDim.x) p.img_off[i] = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) p.img_cur[i] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int b = (int)p.labels[(size_t)t * 6];
+    if (b >= 0 && b < B) atomicAdd(&p.img_off[b + 1], 1);
   }
   __syncthreads();
   // inclusive scan of the counts img_off[1..B], 1024 entries per round
@@ -140,8 +159,6 @@ __global__ void __launch_bounds__(1024) demo_prep_kernel(const DemoParams p) {
     if (b >= 0 && b < B) p.img_list[p.img_off[b] + atomicAdd(&p.img_cur[b], 1)] = t;
   }
   __syncthreads();
-  // the atomic cursors filled every image's list in arbitrary order: sort each (short) list ascending, so that the
-  // duplicate handling of the backward is in target order
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     int* lst = p.img_list + p.img_off[b];
     const int n = p.img_off[b + 1] - p.img_off[b];
@@ -155,6 +172,15 @@ __global__ void __launch_bounds__(1024) demo_prep_kernel(const DemoParams p) {
       lst[j + 1] = v;
     }
   }
+}
+
+// keys (b*A + a)*HW + cell of every (level, target), -1 for rows the loss skips: one thread each
+__global__ void demo_keys_kernel(const DemoParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.T * p.g.L) return;
+  const int l = i / p.T, t = i - l * p.T;
+  const DemoTarget d = demo_target(p.g, l, p.labels + (size_t)t * 6);
+  p.key[(size_t)l * p.T + t] = d.ok ? (d.b * p.g.A + d.a) * p.g.HW[l] + d.gy * p.g.W[l] + d.gx : -1;
 }
 
 // address of channel k of the matched row in the NCHW tensor
@@ -366,38 +392,33 @@ __device__ __forceinline__ void demo_combine(const Geom& g, const double* parts,
   }
 }
 
+// One warp per (level, component): walks its column of per-CTA partials in a fixed order (lane-strided, two loads in flight,
+// shuffle tree) -- no block barrier until the single one before the combine.
 __global__ void __launch_bounds__(1024) demo_finalize_kernel(const DemoParams p) {
-  __shared__ double scratch[32];
-  for (int l = 0; l < p.g.L; ++l) {
-    double v[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = threadIdx.x; i < p.tgt_blocks; i += blockDim.x)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) v[c] += p.tgt_ws[((size_t)l * p.tgt_blocks + i) * 4 + c];
-    double cs = 0.0, cn = 0.0;
-    {
-      const double2* cw = reinterpret_cast<const double2*>(p.cell_ws);
-      const int e = p.cell_cta_begin[l] + p.g.B * p.g.A, st = blockDim.x;
-      int i = p.cell_cta_begin[l] + threadIdx.x;
-      for (; i + 3 * st < e; i += 4 * st) {  // four independent 16-byte loads in flight
-        const double2 a = cw[i], b2 = cw[i + st], c2 = cw[i + 2 * st], d2 = cw[i + 3 * st];
-        cs += (a.x + b2.x) + (c2.x + d2.x);
-        cn += (a.y + b2.y) + (c2.y + d2.y);
-      }
-      for (; i < e; i += st) {
-        const double2 a = cw[i];
-        cs += a.x;
-        cn += a.y;
-      }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = warp / kDemoParts, c = warp - l * kDemoParts;
+  if (l < p.g.L) {
+    // partial slot c of level l: 0..2 <- tgt_ws comps 0..2, 3 <- cell sums, 4 <- cell counts, 5 <- tgt_ws comp 3 (T)
+    const double* col;
+    int n, stride;
+    if (c == 3 || c == 4) {
+      col = p.cell_ws + (size_t)p.cell_cta_begin[l] * 2 + (c - 3);
+      n = p.g.B * p.g.A;
+      stride = 2;
+    } else {
+      col = p.tgt_ws + (size_t)l * p.tgt_blocks * 4 + (c == 5 ? 3 : c);
+      n = p.tgt_blocks;
+      stride = 4;
     }
-    double r[6];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) r[c] = block_sum(v[c], scratch);
-    r[4] = block_sum(cs, scratch);
-    r[5] = block_sum(cn, scratch);
-    if (threadIdx.x == 0) {
-      double* q = p.partials + l * kDemoParts;
-      q[0] = r[0]; q[1] = r[1]; q[2] = r[2]; q[3] = r[4]; q[4] = r[5]; q[5] = r[3];
+    double s0 = 0.0, s1 = 0.0;
+    int i = lane;
+    for (; i + 32 < n; i += 64) {
+      s0 += col[(size_t)i * stride];
+      s1 += col[(size_t)(i + 32) * stride];
     }
+    if (i < n) s0 += col[(size_t)i * stride];
+    const double tot = warp_sum(s0 + s1);
+    if (lane == 0) p.partials[l * kDemoParts + c] = tot;
   }
   __threadfence_block();
   __syncthreads();
@@ -698,6 +719,8 @@ extern "C" int fvb_demo_loss_f32(const fvb_yolo_geom* geom, const float* const* 
   demo_prep_kernel<<<1, 1024, 0, s>>>(p);
   count_launch();
   if (p.T > 0) {
+    demo_keys_kernel<<<(unsigned)(((long long)p.T * p.g.L + 255) / 256), 256, 0, s>>>(p);
+    count_launch();
     dim3 grid((unsigned)L.tgt_blocks, (unsigned)p.g.L);
     demo_targets_kernel<<<grid, kTgtThreads, 0, s>>>(p);
     count_launch();
@@ -779,9 +802,10 @@ extern "C" int fvb_demo_loss_backward_f32(const fvb_yolo_geom* geom, const float
   count_launch();
   if (p.T > 0) {
     demo_prep_kernel<<<1, 1024, 0, s>>>(fp);
+    demo_keys_kernel<<<(unsigned)(((long long)fp.T * fp.g.L + 255) / 256), 256, 0, s>>>(fp);
     dim3 grid((unsigned)L.tgt_blocks, (unsigned)p.g.L);
     demo_grad_targets_kernel<<<grid, kTgtThreads, 0, s>>>(p);
-    count_launch(2);
+    count_launch(3);
   }
   return check_launch("demo_loss_backward");
 }
