@@ -63,6 +63,9 @@ _SIGS = {
     "fvb_yolov3_loss_train_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_float, C.c_float, C.c_float,
                                             _P, _P, _P, _P, _P, _P]),
     "fvb_yolov3_loss_combine_f32": (C.c_int, [C.POINTER(Geom), C.c_int64, _P, C.c_float, C.c_float, C.c_float, _P, _P]),
+    "fvb_peer_buffer_bytes": (C.c_size_t, []),
+    "fvb_yolov3_loss_peer_combine_f32": (C.c_int, [C.POINTER(Geom), C.c_int64, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                   C.c_float, _P, _P, _P, _P]),
     "fvb_yolov3_build_target_f32": (C.c_int, [C.POINTER(Geom), C.c_int, _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P,
                                               _P, _P, _P]),
     "fvb_yolov3_loss_backward_workspace_bytes": (C.c_size_t, [C.POINTER(Geom), C.c_int64]),

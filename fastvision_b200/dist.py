@@ -69,3 +69,55 @@ def all_gather_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
 def gather_map_state(correct_rows: torch.Tensor, target_classes: torch.Tensor, group=None):
     """Bring every rank's mAP evidence together: ``correct`` rows [sum M, 2+n_thr] and target classes [sum N]."""
     return all_gather_rows(correct_rows, group), all_gather_rows(target_classes.view(-1, 1), group).view(-1)
+
+
+# ---- all-reduce + combine of the loss partials over NVLink peer memory ------------------------------------------------------
+_peer_reducers = {}
+
+
+class PeerReducer:
+    """Peer-mapped buffers for ``fvb_yolov3_loss_peer_combine_f32``: one small symmetric-memory allocation per process group,
+    shared by every step object of the process (all ranks must issue the same sequence of reductions on it)."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        nbytes = int(_lib.load().fvb_peer_buffer_bytes())
+        self.buf = symm_mem.empty((nbytes + 7) // 8 + 8, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(self.group)          # every rank's buffer is zeroed and mapped before anybody publishes
+        torch.cuda.synchronize(device)
+
+    def reduce_combine(self, loss_fn, geom, partials, batch_global, out_loss):
+        """In place: ``partials`` <- sum over ranks (same bits everywhere), ``out_loss`` <- the scalar."""
+        from . import _lib
+        lib = _lib.load()
+        with torch.cuda.device(partials.device):
+            _lib.check(lib.fvb_yolov3_loss_peer_combine_f32(geom, int(batch_global), _lib.dptr(partials), _lib.dptr(self.ptrs),
+                                                            self.rank, self.world, float(loss_fn.ratio_box),
+                                                            float(loss_fn.ratio_conf), float(loss_fn.ratio_cls),
+                                                            _lib.dptr(partials), _lib.dptr(out_loss), _lib.dptr(self.status),
+                                                            _lib.stream()), "loss_peer_combine")
+
+
+def peer_reducer(device, group=None) -> Optional["PeerReducer"]:
+    """The process-wide PeerReducer of ``group`` (created collectively on first use), or None when symmetric memory is not
+    available / FVB_PEER_REDUCE=0 -- callers then fall back to the NCCL all-reduce + combine."""
+    import os
+    if os.environ.get("FVB_PEER_REDUCE", "1") == "0":
+        return None
+    key = (id(group), device.index)
+    if key not in _peer_reducers:
+        try:
+            _peer_reducers[key] = PeerReducer(device, group)
+        except Exception as exc:  # symmetric memory unsupported on this system: NCCL path
+            import warnings
+            warnings.warn("fastvision_b200: peer-memory reduce unavailable (%s); using NCCL all-reduce" % (exc,))
+            _peer_reducers[key] = None
+    return _peer_reducers[key]

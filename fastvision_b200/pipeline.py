@@ -43,6 +43,7 @@ class ValStep:
         self._side = None
         self._ev_decoded = None
         self._ev_loss = None
+        self._peer_reducer = False       # not looked up yet
 
     def _prepare(self, heads):
         ctx = DecodeContext(heads, self.anchors_per_level, self.strides)
@@ -103,9 +104,20 @@ class ValStep:
         if not self._distributed():
             return
         o, ctx = self.out, self.ctx
-        torch.distributed.all_reduce(o["partials"], group=self.pg)
         bg = self.batch_global or ctx.batch * torch.distributed.get_world_size(self.pg)
+        peer = self._peer()
+        if peer is not None:
+            # one single-CTA kernel over NVLink peer memory: publish, wait for the peers, sum in rank order, combine
+            peer.reduce_combine(self.loss_fn, ctx.geom, o["partials"], bg, o["loss"])
+            return
+        torch.distributed.all_reduce(o["partials"], group=self.pg)
         self.loss_fn.combine(o["partials"], bg, ctx=ctx, out=o["loss"])
+
+    def _peer(self):
+        if self._peer_reducer is False:
+            from .dist import peer_reducer
+            self._peer_reducer = peer_reducer(self.ctx.device, self.pg) if torch.distributed.get_backend(self.pg) == "nccl" else None
+        return self._peer_reducer
 
     def _run(self, heads, labels):
         self._decode(heads)
@@ -132,11 +144,14 @@ class ValStep:
         heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
         labels = _lib.require_cuda(labels, "labels").view(-1, 6)
         self._prepare(heads)
+        dist_graph = False
         if self._distributed():
-            # data-parallel: keep the NCCL all-reduce out of any graph and inside the loss branch (overlaps the NMS)
-            if split_decode:
-                return (lambda: self._decode(heads)), (lambda: self._tail(heads, labels, reduce_inside=True))
-            return lambda: self._run(heads, labels)
+            if self._peer() is None:
+                # NCCL fallback: keep the all-reduce out of any graph and inside the loss branch (overlaps the NMS)
+                if split_decode:
+                    return (lambda: self._decode(heads)), (lambda: self._tail(heads, labels, reduce_inside=True))
+                return lambda: self._run(heads, labels)
+            dist_graph = True    # the peer-memory reduce is an ordinary kernel: the whole step can be captured
         warm = torch.cuda.Stream(device=self.ctx.device)
         warm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(warm):
@@ -148,7 +163,7 @@ class ValStep:
         with torch.cuda.graph(g):
             if not split_decode:
                 self._decode(heads)
-            self._tail(heads, labels)
+            self._tail(heads, labels, reduce_inside=dist_graph)
         self.graph = g
 
         if split_decode:

@@ -215,6 +215,17 @@ int fvb_yolov3_loss_train_f32(const fvb_yolo_geom* geom, const float* const* d_h
 int fvb_yolov3_loss_combine_f32(const fvb_yolo_geom* geom, int64_t batch_global, const double* d_partials,
                                 float ratio_box, float ratio_conf, float ratio_cls, float* d_out_loss,
                                 void* stream);
+/* Data-parallel finish over NVLink peer memory: all-reduce of the [L*4] partials over `world` ranks fused with
+ * the combine, one single-CTA kernel (replaces ncclAllReduce(96 B) + fvb_yolov3_loss_combine_f32; capturable in a CUDA graph).
+ * d_peer_ptrs: device array [world] of the base addresses of every rank's peer buffer (fvb_peer_buffer_bytes() bytes, ZEROED
+ * once before first use, mapped into this process -- torch symmetric memory provides them).  Every rank must make the same
+ * sequence of calls on one buffer set.  d_partials_out [L*4] receives the global sums (same bits on all ranks), d_out_loss the
+ * scalar; d_status (may be NULL) 0, or 1 if a peer did not arrive within ~2 s (loss := NaN, no hang). */
+size_t fvb_peer_buffer_bytes(void);
+int fvb_yolov3_loss_peer_combine_f32(const fvb_yolo_geom* geom, int64_t batch_global, const double* d_partials,
+                                     const uint64_t* d_peer_ptrs, int rank, int world, float ratio_box, float ratio_conf,
+                                     float ratio_cls, double* d_partials_out, float* d_out_loss, int32_t* d_status,
+                                     void* stream);
 /* Yolov3Loss.build_target, loss/yolov3_loss.py:75-124, for one level: padded outputs of T*A rows in
  * (t,a) row-major order with d_match[T*A] u8 flags; d_count[1] int32 = M.  Compacted (matches first,
  * order kept) when compact != 0. */

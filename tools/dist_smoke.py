@@ -37,6 +37,16 @@ out = step(dh, dl)
 torch.cuda.synchronize()
 loss_sharded = float(out["loss"])
 log("eager loss %.6f" % loss_sharded)
+log("peer reduce active: %s" % (step._peer() is not None))
+nccl_step = ValStep(cfg.anchors_levels(), cfg.strides, batch_global=batch)
+nccl_step._peer_reducer = None                     # force the NCCL all-reduce + combine path
+o2 = nccl_step(dh, dl)
+torch.cuda.synchronize()
+log("NCCL-path loss %.6f (peer path %.6f)" % (float(o2["loss"]), loss_sharded))
+assert abs(float(o2["loss"]) - loss_sharded) <= 1e-6 * abs(loss_sharded)
+assert torch.allclose(o2["partials"], out["partials"], rtol=1e-12)
+if step._peer() is not None:
+    assert int(step._peer().status[0]) == 0
 log("capture")
 replay = step.capture(dh, dl)
 log("replay")
