@@ -355,6 +355,14 @@ def run_cuda(args, cfg):
     pipelined_ms = float(tp.item()) / kp
     del pipe
 
+    if not distributed:
+        step_launch = "decode launched eagerly between CUDA events, NMS + loss branches replayed as a CUDA graph"
+    elif step._peer() is not None:
+        step_launch = ("decode launched eagerly between CUDA events; NMS branch and loss branch (+ the single-kernel all-reduce + "
+                       "combine of the 12 fp64 partials over NVLink peer memory) replayed as a CUDA graph")
+    else:
+        step_launch = ("decode launched eagerly between CUDA events; NMS branch and loss branch (+ NCCL all-reduce of the 12 fp64 "
+                       "partials) launched eagerly on two streams")
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         rows = step.ctx.rows
@@ -379,9 +387,7 @@ def run_cuda(args, cfg):
                        "conf_thres": 0.25, "iou_thres": 0.45, "max_det": 300, "loss_ratios": [0.05, 1.0, 0.5],
                        "labels": int(labels.size(0)), "parallelism": "per-image sharding, dp%d" % world,
                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2; no flush needed" % (alg_bytes / 2e6),
-                       "step_launch": ("decode launched eagerly between CUDA events; NMS branch and loss branch (+ NCCL all-reduce of the "
-                                       "12 fp64 partials) launched eagerly on two streams" if distributed else
-                                       "decode launched eagerly between CUDA events, NMS + loss branches replayed as a CUDA graph"),
+                       "step_launch": step_launch,
                        "pipelined_extra": {"ms_per_step": pipelined_ms, "images_per_s": batch * world / (pipelined_ms * 1e-3), "steps": kp,
                                            "note": "ValPipeline: NMS + loss of batch i overlap the decode of batch i+1 (two buffer sets); "
                                                    "not the headline because the co-running tail slows the decode kernel"}},
