@@ -32,10 +32,10 @@ def make_pred(g, n, classes):
     pred = torch.cat([xy, wh, conf, cls], 1)
     m = max(1, n // 6)
     idx = torch.randint(0, n, (m,), generator=g)
-    pred[idx] = pred[idx.roll(1)]                                   # exact duplicates: coincident boxes + score ties
+    pred[idx] = pred[idx.roll(1)].clone()                                   # exact duplicates: coincident boxes + score ties
     pred[torch.randint(0, n, (2,), generator=g), 2] = 0.0            # zero width
     t = torch.randint(0, n, (m,), generator=g)
-    pred[t, 4] = pred[t[0], 4]                                       # objectness ties
+    pred[t, 4] = float(pred[t[0], 4])                                       # objectness ties
     return pred
 
 
