@@ -18,43 +18,70 @@ __global__ void iou_elementwise_kernel(const float* a, const float* b, long long
   out[i] = iou_family<false>(ba, bb, kind, variant, eps);
 }
 
-constexpr int kPairRows = 32, kPairCols = 128;
+constexpr int kPairRows = 64, kPairCols = 128;
 
-// Pairwise tile kernel: the CTA stages 32 "a" boxes and 128 "b" boxes (already xyxy) in shared
-// memory, each thread owns one column and 16 rows; stores are coalesced along M.
-__global__ void __launch_bounds__(256) iou_pairwise_kernel(const float* a, long long n, const float* b, long long m,
-                                                           int box_mode, int kind, int variant, float eps, float* out) {
-  __shared__ Box sa[kPairRows];
-  __shared__ Box sb[kPairCols];
-  const long long r0 = (long long)blockIdx.y * kPairRows, c0 = (long long)blockIdx.x * kPairCols;
+// Pairwise tile kernel.  A CTA owns a strip of 128 "b" boxes (one per thread column, in registers) and walks its share of the
+// "a" boxes in tiles of 64 staged in shared memory (double-buffered: the next tile is fetched while the current one is
+// computed, one barrier per tile); thread (col, half) computes 32 pairs per tile; every store instruction of a warp writes
+// 128 contiguous bytes of one output row.  KIND is a template parameter: no per-pair dispatch.  (The first version gave every
+// CTA 32 x 128 pairs: 16 pairs per thread behind a global load + barrier -- latency-bound at 24 % of the HBM write peak.)
+template <int KIND, bool WH>
+__global__ void __launch_bounds__(256) iou_pairwise_kernel(const float* __restrict__ a, long long n, const float* __restrict__ b,
+                                                           long long m, int box_mode, int variant, float eps,
+                                                           float* __restrict__ out, long long rows_per_cta) {
+  __shared__ Box sa[2][kPairRows];
+  const long long c0 = (long long)blockIdx.x * kPairCols;
+  const long long row_beg = (long long)blockIdx.y * rows_per_cta, row_end = min(n, row_beg + rows_per_cta);
   const int tid = threadIdx.x;
-  if (tid < kPairRows && r0 + tid < n) {
-    if (box_mode == FVB_BOX_WH) {
-      Box t; t.x1 = a[(r0 + tid) * 2]; t.y1 = a[(r0 + tid) * 2 + 1]; t.x2 = 0; t.y2 = 0;
-      sa[tid] = t;
-    } else {
-      sa[tid] = load_box(a + (r0 + tid) * 4, box_mode);
+  const int col = tid & (kPairCols - 1), half = tid / kPairCols;  // 2 row phases
+  const bool col_ok = c0 + col < m;
+  auto load_a = [&](long long r) -> Box {
+    if (WH) {
+      Box t; t.x1 = a[r * 2]; t.y1 = a[r * 2 + 1]; t.x2 = 0; t.y2 = 0;
+      return t;
     }
+    return load_box(a + r * 4, box_mode);
+  };
+  Box bb;
+  bb.x1 = bb.y1 = bb.x2 = bb.y2 = 0.0f;
+  if (col_ok) {
+    if (WH) { bb.x1 = b[(c0 + col) * 2]; bb.y1 = b[(c0 + col) * 2 + 1]; }
+    else bb = load_box(b + (c0 + col) * 4, box_mode);
   }
-  if (tid >= 128 && tid - 128 < kPairCols && c0 + tid - 128 < m) {
-    int j = tid - 128;
-    if (box_mode == FVB_BOX_WH) {
-      Box t; t.x1 = b[(c0 + j) * 2]; t.y1 = b[(c0 + j) * 2 + 1]; t.x2 = 0; t.y2 = 0;
-      sb[j] = t;
-    } else {
-      sb[j] = load_box(b + (c0 + j) * 4, box_mode);
-    }
-  }
+  if (row_beg >= row_end) return;
+  if (tid < kPairRows && row_beg + tid < row_end) sa[0][tid] = load_a(row_beg + tid);
   __syncthreads();
-  const int col = tid & (kPairCols - 1), rsub = tid / kPairCols;  // 2 row phases
-  if (c0 + col >= m) return;
-  const Box bb = sb[col];
-#pragma unroll 4
-  for (int r = rsub; r < kPairRows; r += 256 / kPairCols) {
-    if (r0 + r >= n) break;
-    const Box ba = sa[r];
-    float v = (box_mode == FVB_BOX_WH) ? wh_iou(ba.x1, ba.y1, bb.x1, bb.y1, eps) : iou_family<true>(ba, bb, kind, variant, eps);
-    out[(r0 + r) * m + c0 + col] = v;
+  int buf = 0;
+  for (long long r0 = row_beg; r0 < row_end; r0 += kPairRows, buf ^= 1) {
+    // prefetch the next tile into registers; it lands in the other buffer after this tile's pairs
+    const long long rn = r0 + kPairRows + tid;
+    Box nxt;
+    const bool have_next = tid < kPairRows && rn < row_end;
+    if (have_next) nxt = load_a(rn);
+    const int rows = (int)min((long long)kPairRows, row_end - r0);
+    if (col_ok) {
+      float* o = out + (r0 + half) * m + c0 + col;
+      const long long step = (long long)(256 / kPairCols) * m;
+      if (rows == kPairRows) {
+        // full tile: fixed trip count, no bounds checks in the pair loop
+#pragma unroll 8
+        for (int i = 0; i < kPairRows / (256 / kPairCols); ++i) {
+          const Box ba = sa[buf][half + i * (256 / kPairCols)];
+          const float v = WH ? wh_iou(ba.x1, ba.y1, bb.x1, bb.y1, eps) : iou_family<true>(ba, bb, KIND, variant, eps);
+          __stcs(o, v);
+          o += step;
+        }
+      } else {
+        for (int r = half; r < rows; r += 256 / kPairCols) {
+          const Box ba = sa[buf][r];
+          const float v = WH ? wh_iou(ba.x1, ba.y1, bb.x1, bb.y1, eps) : iou_family<true>(ba, bb, KIND, variant, eps);
+          __stcs(o, v);
+          o += step;
+        }
+      }
+    }
+    if (have_next) sa[buf ^ 1][tid] = nxt;
+    __syncthreads();
   }
 }
 
@@ -195,10 +222,24 @@ extern "C" int fvb_iou_pairwise_f32(const float* d_a, int64_t n, const float* d_
   FVB_REQUIRE(n >= 0 && m >= 0, "iou_pairwise: negative size");
   if (n == 0 || m == 0) return FVB_OK;
   FVB_REQUIRE(d_a && d_b && d_out, "iou_pairwise: NULL pointer");
-  long long gy = (n + kPairRows - 1) / kPairRows;
-  FVB_REQUIRE(gy <= 65535, "iou_pairwise: N=%lld too large for one launch", (long long)n);
-  dim3 grid((unsigned)((m + kPairCols - 1) / kPairCols), (unsigned)gy);
-  iou_pairwise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, n, d_b, m, box_mode, kind, variant, eps, d_out);
+  const long long strips = (m + kPairCols - 1) / kPairCols;
+  FVB_REQUIRE(strips < (1ll << 31), "iou_pairwise: M=%lld too large for one launch", (long long)m);
+  // enough CTAs to fill the machine (~8 per SM), each walking a contiguous share of the rows in tiles of kPairRows
+  const long long tiles = (n + kPairRows - 1) / kPairRows;
+  long long splits = (1184 + strips - 1) / strips;
+  if (splits > tiles) splits = tiles;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  const long long rows_per_cta = ((tiles + splits - 1) / splits) * kPairRows;
+  dim3 grid((unsigned)strips, (unsigned)((n + rows_per_cta - 1) / rows_per_cta));
+  cudaStream_t st = (cudaStream_t)stream;
+#define FVB_PAIR(KIND_, WH_) iou_pairwise_kernel<KIND_, WH_><<<grid, 256, 0, st>>>(d_a, n, d_b, m, box_mode, variant, eps, d_out, rows_per_cta)
+  if (box_mode == FVB_BOX_WH) FVB_PAIR(FVB_IOU, true);
+  else if (kind == FVB_IOU) FVB_PAIR(FVB_IOU, false);
+  else if (kind == FVB_GIOU) FVB_PAIR(FVB_GIOU, false);
+  else if (kind == FVB_DIOU) FVB_PAIR(FVB_DIOU, false);
+  else FVB_PAIR(FVB_CIOU, false);
+#undef FVB_PAIR
   count_launch();
   return check_launch("iou_pairwise_kernel");
 }
