@@ -103,16 +103,27 @@ __device__ inline unsigned long long* block_radix_sort_hi32(unsigned long long* 
   for (int shift = 32; shift < 64; shift += 8) {
     for (int i = threadIdx.x; i < kNmsWarps * 256; i += kNmsThreads) cnt[i] = 0;
     __syncthreads();
-    for (int base = beg; base < end; base += 32) {
-      int i = base + lane;
-      bool act = i < end;
-      unsigned m = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        uint32_t d = (uint32_t)(src[i] >> shift) & 255u;
-        unsigned peers = __match_any_sync(m, d);
-        if (lane == __ffs(peers) - 1) cnt[d * kNmsWarps + warp] += __popc(peers);
+    // keys may live in global memory (more candidates than the shared-memory capacity, e.g. the RPN's 22 500 anchors): four
+    // batches of 32 keys are loaded before any of them is counted, so the loop is not one L2 round trip per 32 keys
+    for (int base = beg; base < end; base += 128) {
+      unsigned long long k4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        k4[u] = i < end ? src[i] : 0ull;
       }
-      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        const bool act = i < end;
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (act) {
+          const uint32_t d = (uint32_t)(k4[u] >> shift) & 255u;
+          const unsigned peers = __match_any_sync(m, d);
+          if (lane == __ffs(peers) - 1) cnt[d * kNmsWarps + warp] += __popc(peers);
+        }
+        __syncwarp();
+      }
     }
     __syncthreads();
     {
@@ -131,22 +142,31 @@ __device__ inline unsigned long long* block_radix_sort_hi32(unsigned long long* 
       }
     }
     __syncthreads();
-    for (int base = beg; base < end; base += 32) {
-      int i = base + lane;
-      bool act = i < end;
-      unsigned m = __ballot_sync(0xffffffffu, act);
-      uint32_t d = 0;
-      unsigned peers = 0;
-      if (act) {
-        unsigned long long key = src[i];
-        d = (uint32_t)(key >> shift) & 255u;
-        peers = __match_any_sync(m, d);
-        uint32_t pos = cnt[d * kNmsWarps + warp] + __popc(peers & lt_mask);
-        dst[pos] = key;
+    for (int base = beg; base < end; base += 128) {
+      unsigned long long k4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        k4[u] = i < end ? src[i] : 0ull;
       }
-      __syncwarp();
-      if (act && lane == __ffs(peers) - 1) cnt[d * kNmsWarps + warp] += __popc(peers);
-      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        const bool act = i < end;
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        uint32_t d = 0;
+        unsigned peers = 0;
+        if (act) {
+          const unsigned long long key = k4[u];
+          d = (uint32_t)(key >> shift) & 255u;
+          peers = __match_any_sync(m, d);
+          const uint32_t pos = cnt[d * kNmsWarps + warp] + __popc(peers & lt_mask);
+          dst[pos] = key;
+        }
+        __syncwarp();
+        if (act && lane == __ffs(peers) - 1) cnt[d * kNmsWarps + warp] += __popc(peers);
+        __syncwarp();
+      }
     }
     __syncthreads();
     unsigned long long* t = src;
