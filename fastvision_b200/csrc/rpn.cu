@@ -11,7 +11,9 @@
 // Ties: equal scores rank by lower anchor index (torch.topk leaves tie order unspecified).
 #include "nms.cuh"
 
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace fvb {
 
@@ -109,6 +111,216 @@ __global__ void __launch_bounds__(kNmsThreads) rpn_nms_kernel(const RpnParams p)
   if (threadIdx.x == 0) p.out_cnt[b] = kept;
 }
 
+// ---- thread-block-cluster variant: two CTAs (two SMs) per image ---------------------------------------------------------------
+// With pre_n = 12000 / post_n = 2000 the greedy pass is ~12 M pair tests per image, fp32-issue-bound on the ONE SM the image's
+// CTA runs on, and a batch of 64 images leaves 84 of the 148 SMs idle.  Here a cluster of kRpnCluster CTAs shares an image: the
+// kept list is dealt round-robin over the CTAs (kept i lives in CTA i % C), every CTA tests the 64-candidate chunk against
+// ITS slice only, the partial "still alive" masks are exchanged through distributed shared memory (each CTA stores its 64-bit
+// partial into every peer's exchange slot, one hardware cluster barrier per chunk) and AND-ed; the cheap intra-chunk mask and
+// the serial resolve are replicated, so all CTAs take identical decisions and append identical kept indices (each keeps its
+// own share).  The keep set is exactly the sequential algorithm's.
+namespace cg = cooperative_groups;
+constexpr int kRpnCluster = 2;
+
+struct RpnClusterSmem {
+  size_t cnt, warp_tot, kbox, karea, kslot, gs, xalive, total;
+};
+__host__ __device__ inline RpnClusterSmem rpn_cluster_layout(int max_keep) {
+  RpnClusterSmem L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    o = (o + 15) / 16 * 16;
+    size_t r = o;
+    o += bytes;
+    return r;
+  };
+  const int local = (max_keep + kRpnCluster - 1) / kRpnCluster + 1;
+  L.cnt = take((size_t)kNmsWarps * 256 * 4);
+  L.warp_tot = take((size_t)(kNmsWarps + 1) * 4);
+  L.kbox = take((size_t)local * 16);
+  L.karea = take((size_t)local * 4);
+  L.kslot = take((size_t)local * 4);
+  L.gs = take(sizeof(GreedyShared));
+  L.xalive = take((size_t)2 * kRpnCluster * 2 * 4);  // [chunk parity][source rank][word]
+  L.total = o;
+  return L;
+}
+
+__global__ void __cluster_dims__(kRpnCluster, 1, 1) __launch_bounds__(kNmsThreads) rpn_nms_cluster_kernel(const RpnParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const RpnClusterSmem L = rpn_cluster_layout(p.post_n);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L.cnt);
+  uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + L.warp_tot);
+  float4* kbox = reinterpret_cast<float4*>(smem + L.kbox);      // my slice: kept i with i % C == rank, at i / C
+  float* karea = reinterpret_cast<float*>(smem + L.karea);
+  int* kslot = reinterpret_cast<int*>(smem + L.kslot);
+  GreedyShared* gs = reinterpret_cast<GreedyShared*>(smem + L.gs);
+  unsigned* xalive = reinterpret_cast<unsigned*>(smem + L.xalive);
+  const int b = blockIdx.x / kRpnCluster;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+  unsigned long long* keys0 = p.keys + (size_t)b * 2 * p.n;
+  const float4* box = p.box + (size_t)b * p.n;
+  // the sort is one CTA's job (both buffers of the image are shared); its result is published by the cluster barrier
+  __shared__ const unsigned long long* s_sorted;
+  if (rank == 0) {
+    const unsigned long long* srt = block_radix_sort_hi32(keys0, keys0 + p.n, p.n, cnt, warp_tot);
+    if (tid == 0) s_sorted = srt;
+  }
+  __threadfence();
+  cluster.sync();
+  const unsigned long long* sorted = *cluster.map_shared_rank(&s_sorted, 0);
+  const int n = min(p.pre_n, p.n);  // rpn.py:193-195 topk
+  const int max_keep = p.post_n;
+  const float thr = p.iou_thr;
+  const NmsFast fast = make_nms_fast(thr);
+  unsigned* peer_x[kRpnCluster];
+#pragma unroll
+  for (int r = 0; r < kRpnCluster; ++r) peer_x[r] = cluster.map_shared_rank(xalive, r);
+
+  if (tid == 0) {
+    gs->kcount = 0;
+    const int cn0 = min(kNmsChunk, n);
+    gs->alive32[0] = cn0 >= 32 ? 0xffffffffu : ((1u << cn0) - 1u);
+    gs->alive32[1] = cn0 >= 64 ? 0xffffffffu : (cn0 > 32 ? ((1u << (cn0 - 32)) - 1u) : 0u);
+    gs->nz32[0] = gs->nz32[1] = 0u;
+  }
+  if (tid < kNmsChunk) stage_chunk(gs, 0, sorted, 0, n, box, tid);
+  __syncthreads();
+  int buf = 0;
+  for (int c0 = 0; c0 < n; c0 += kNmsChunk, buf ^= 1) {
+    const int kc = gs->kcount;  // replicated: identical in every CTA of the cluster
+    if (kc >= max_keep) break;
+    const int cn = min(kNmsChunk, n - c0);
+    const int kl = (kc - rank + kRpnCluster - 1) / kRpnCluster;  // kept boxes in my slice
+    // (a) the chunk against MY slice of the kept list
+    {
+      const int r = tid & (kNmsChunk - 1), s = tid / kNmsChunk;
+      constexpr int S = kNmsThreads / kNmsChunk;
+      if (r < cn && s < kl) {
+        const float4 bj = gs->cbox[buf][r];
+        const float aj = gs->carea[buf][r];
+        bool hit = false;
+        if (fast.ok) {
+          bool amb = false;
+          int i = s;
+          for (; i + S < kl; i += 2 * S) {
+            const float4 k0 = kbox[i], k1 = kbox[i + S];
+            const float a0 = karea[i], a1 = karea[i + S];
+            nms_overlap_fast(k0, a0, bj, aj, fast, hit, amb);
+            nms_overlap_fast(k1, a1, bj, aj, fast, hit, amb);
+          }
+          if (i < kl) nms_overlap_fast(kbox[i], karea[i], bj, aj, fast, hit, amb);
+          if (amb && !hit) {
+            for (i = s; i < kl; i += S)
+              if (nms_overlap(kbox[i], karea[i], bj, aj, thr)) {
+                hit = true;
+                break;
+              }
+          }
+        } else {
+          for (int i = s; i < kl; i += S)
+            if (nms_overlap(kbox[i], karea[i], bj, aj, thr)) {
+              hit = true;
+              break;
+            }
+        }
+        if (hit) atomicAnd(&gs->alive32[r >> 5], ~(1u << (r & 31)));
+      }
+    }
+    // (b) intra-chunk mask (replicated in every CTA: 64 x 64 tests, small next to (a))
+    for (int r = warp; r < cn; r += kNmsWarps) {
+      const float4 br = gs->cbox[buf][r];
+      const float ar = gs->carea[buf][r];
+      unsigned long long row = 0ull;
+#pragma unroll
+      for (int h = 0; h < kNmsChunk / 32; ++h) {
+        const int q = h * 32 + lane;
+        bool hit = false;
+        if (q > r && q < cn) {
+          const float4 bq = gs->cbox[buf][q];
+          const float aq = gs->carea[buf][q];
+          if (fast.ok) {
+            bool amb = false;
+            nms_overlap_fast(br, ar, bq, aq, fast, hit, amb);
+            if (amb && !hit) hit = nms_overlap(br, ar, bq, aq, thr);
+          } else {
+            hit = nms_overlap(br, ar, bq, aq, thr);
+          }
+        }
+        const unsigned w = __ballot_sync(0xffffffffu, hit);
+        row |= (unsigned long long)w << (32 * h);
+      }
+      if (lane == 0) {
+        gs->mask[r] = row;
+        if (row) atomicOr(&gs->nz32[r >> 5], 1u << (r & 31));
+      }
+    }
+    __syncthreads();
+    // exchange the partial alive masks: my two words go into slot [buf][rank] of every CTA of the cluster (DSMEM stores)
+    if (tid < 2 * kRpnCluster) {
+      const int dst = tid >> 1, w = tid & 1;
+      peer_x[dst][(buf * kRpnCluster + rank) * 2 + w] = gs->alive32[w];
+    }
+    cluster.sync();
+    // (c) resolve on warp 0 with the AND of all partials; warps 1-2 stage the next chunk
+    if (warp == 0) {
+      unsigned a0 = 0xffffffffu, a1 = 0xffffffffu;
+#pragma unroll
+      for (int r = 0; r < kRpnCluster; ++r) {
+        a0 &= xalive[(buf * kRpnCluster + r) * 2 + 0];
+        a1 &= xalive[(buf * kRpnCluster + r) * 2 + 1];
+      }
+      unsigned long long remaining = ((unsigned long long)a1 << 32) | a0;
+      const unsigned long long nz = ((unsigned long long)gs->nz32[1] << 32) | gs->nz32[0];
+      unsigned long long todo = remaining & nz;
+      while (todo) {  // warp-uniform
+        const int j = __ffsll((long long)todo) - 1;
+        remaining &= ~gs->mask[j];
+        todo = remaining & nz & ~((2ull << j) - 1ull);
+      }
+      const unsigned long long kept = remaining;
+      const int room = max_keep - kc;
+#pragma unroll
+      for (int h = 0; h < kNmsChunk / 32; ++h) {
+        const int q = h * 32 + lane;
+        if ((kept >> q) & 1ull) {
+          const int rk = __popcll(kept & ((1ull << q) - 1ull));
+          const int gidx = kc + rk;  // position in the (virtual) global kept list
+          if (rk < room && gidx % kRpnCluster == rank) {
+            const int li = gidx / kRpnCluster;
+            kbox[li] = gs->cbox[buf][q];
+            karea[li] = gs->carea[buf][q];
+            kslot[li] = gs->cslot[buf][q];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        gs->kcount = kc + min(room, __popcll(kept));
+        const int cn1 = min(kNmsChunk, max(0, n - c0 - kNmsChunk));
+        gs->alive32[0] = cn1 >= 32 ? 0xffffffffu : ((1u << cn1) - 1u);
+        gs->alive32[1] = cn1 >= 64 ? 0xffffffffu : (cn1 > 32 ? ((1u << (cn1 - 32)) - 1u) : 0u);
+        gs->nz32[0] = gs->nz32[1] = 0u;
+      }
+    } else if (warp <= kNmsChunk / 32) {
+      stage_chunk(gs, buf ^ 1, sorted, c0 + kNmsChunk, n, box, tid - 32);
+    }
+    __syncthreads();
+  }
+  const int kept = gs->kcount;
+  for (int i = rank + kRpnCluster * tid; i < kept; i += kRpnCluster * kNmsThreads) {
+    const int li = i / kRpnCluster;
+    const float4 q = kbox[li];
+    const float4 o = make_float4((q.x + q.z) / 2.0f, (q.y + q.w) / 2.0f, q.z - q.x, q.w - q.y);  // rpn.py:139-145
+    reinterpret_cast<float4*>(p.out_xywh)[(size_t)b * p.out_pitch + i] = o;
+    if (p.out_idx) p.out_idx[(size_t)b * p.out_pitch + i] = kslot[li];
+  }
+  if (rank == 0 && tid == 0) p.out_cnt[b] = kept;
+  cluster.sync();  // no CTA may exit while a peer can still address its shared memory
+}
+
 static size_t rpn_align(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace fvb
@@ -160,6 +372,28 @@ extern "C" int fvb_rpn_proposals_f32(const float* d_cls, const float* d_reg, con
   p.out_idx = d_out_idx;
   p.out_cnt = d_out_cnt;
   p.out_pitch = post_n;
+  cudaStream_t cs = (cudaStream_t)stream;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)batch);
+  rpn_decode_kernel<<<grid, 256, 0, cs>>>(p);
+  count_launch();
+  // long greedy passes (many candidates, many proposals kept) run on a 2-CTA cluster per image; FVB_RPN_CLUSTER=0/1 overrides
+  bool use_cluster = (pre_n < n ? pre_n : n) >= 4096 && p.post_n >= 1024;
+  if (const char* e = getenv("FVB_RPN_CLUSTER")) use_cluster = e[0] == '1';
+  if (use_cluster) {
+    RpnClusterSmem LC = rpn_cluster_layout(p.post_n);
+    if (LC.total > 227 * 1024) {
+      set_error("rpn_proposals: post_n=%d needs %zu bytes of shared memory for the kept list", post_n, LC.total);
+      return FVB_E_LIMIT;
+    }
+    cudaError_t e = cudaFuncSetAttribute((const void*)rpn_nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC.total);
+    if (e != cudaSuccess) {
+      set_error("rpn_proposals: cudaFuncSetAttribute(%zu): %s", LC.total, cudaGetErrorString(e));
+      return FVB_E_CUDA;
+    }
+    rpn_nms_cluster_kernel<<<batch * kRpnCluster, kNmsThreads, LC.total, cs>>>(p);
+    count_launch();
+    return check_launch("rpn_nms_cluster_kernel");
+  }
   RpnSmemLayout L = rpn_layout(p.post_n);
   if (L.total > 227 * 1024) {
     set_error("rpn_proposals: post_n=%d needs %zu bytes of shared memory for the kept list", post_n, L.total);
@@ -170,10 +404,6 @@ extern "C" int fvb_rpn_proposals_f32(const float* d_cls, const float* d_reg, con
     set_error("rpn_proposals: cudaFuncSetAttribute(%zu): %s", L.total, cudaGetErrorString(e));
     return FVB_E_CUDA;
   }
-  cudaStream_t cs = (cudaStream_t)stream;
-  dim3 grid((unsigned)((n + 255) / 256), (unsigned)batch);
-  rpn_decode_kernel<<<grid, 256, 0, cs>>>(p);
-  count_launch();
   rpn_nms_kernel<<<batch, kNmsThreads, L.total, cs>>>(p);
   count_launch();
   return check_launch("rpn_nms_kernel");

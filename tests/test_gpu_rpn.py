@@ -124,3 +124,30 @@ def test_rpn_errors():
         ft.filter_proposals(torch.zeros(1, 2, 2, 1, 2), torch.zeros(1, 2, 2, 1, 4), base)      # CPU tensors: no fallback
     with pytest.raises(ValueError):
         ft.filter_proposals(torch.zeros(1, 2, 2, 2, 2).cuda(), torch.zeros(1, 2, 2, 2, 4).cuda(), base)
+
+
+@pytest.mark.parametrize("cluster", ["0", "1"])
+def test_rpn_cluster_and_single_cta_paths_agree(golden_rpn, cluster, monkeypatch):
+    """The 2-CTA thread-block-cluster greedy (kept list dealt over the CTAs, partial alive masks exchanged through distributed
+    shared memory) and the one-CTA-per-image kernel return the same proposals: golden cases and a config-4 shaped batch."""
+    monkeypatch.setenv("FVB_RPN_CLUSTER", cluster)
+    for tag in ("a", "b"):
+        g = golden_rpn
+        pre, post, thr = g[tag + "_cfg"]
+        cls, reg = T(g[tag + "_cls"]), T(g[tag + "_reg"])
+        fh, fw = cls.size(1), cls.size(2)
+        base = T(g["base_anchors_px"]) / 16
+        anc = ft.make_anchors_xywh(base.cuda(), fh, fw)
+        props = ft.filter_proposals(cls.cuda(), reg.cuda(), anc, fh, fw, int(pre), int(post), float(thr))
+        for i, pr in enumerate(props):
+            close(pr, g["%s_prop%d" % (tag, i)])
+    gen = synth.make_generator(4, 7)
+    cls, reg = synth.make_rpn_inputs(5, 50, 50, 9, gen)
+    base = ft.get_base_anchor([128, 256, 512], [1, 0.5, 2]) / 16
+    out, cnt, idx = ft.filter_proposals_batched(cls.cuda(), reg.cuda(), base, 12000, 2000, 0.7, want_idx=True)
+    monkeypatch.setenv("FVB_RPN_CLUSTER", "0")
+    out0, cnt0, idx0 = ft.filter_proposals_batched(cls.cuda(), reg.cuda(), base, 12000, 2000, 0.7, want_idx=True)
+    assert torch.equal(cnt, cnt0)
+    for i in range(5):
+        k = int(cnt[i])
+        assert torch.equal(idx[i, :k], idx0[i, :k]) and torch.equal(out[i, :k], out0[i, :k])
