@@ -1,0 +1,113 @@
+"""``Fit`` -- drop-in for the caller glue of the hot path, utils/fit.py:12-105.
+
+``_train`` is the reference's loop (utils/fit.py:47-71); with the drop-in ``Yolov3Loss`` its ``loss.backward()`` runs the
+hand-written backward kernels.  ``_val`` (utils/fit.py:73-105) keeps the reference's semantics -- loss of every batch,
+per-image confidence filter + NMS, per-image mAP matching, ``fetch`` at the end -- but runs the fused step: one decode kernel
+(the model is asked for the raw heads only), NMS of all images in one launch, the loss branch beside it, one matcher launch per
+batch and the AP integration on the device; the reference's per-image Python loop with >= 3 host syncs per image is gone.
+Checkpoint writing (fastvision.utils.checkpoints.SaveModel, out of scope) is an optional ``save_fn`` callback.
+"""
+import numpy as np
+import torch
+
+from ..metrics import CalculateMAP
+from ..pipeline import ValStep
+
+
+class Fit():
+
+    def __init__(self, model, device, optimizer, scheduler, loss, end_epoch, start_epoch=0, train_loader=None, val_loader=None,
+                 test_loader=None, data_dict=None, save_fn=None, verbose=True):
+        self.model = model
+        self.device = device
+        self.optimizer = optimizer
+        self.loss = loss
+        self.start_epoch = start_epoch
+        self.end_epoch = end_epoch
+        self.train_loader = train_loader
+        self.val_loader = val_loader
+        self.test_loader = test_loader
+        self.scheduler = scheduler
+        self.category_names = {k: v for k, v in enumerate((data_dict or {}).get('categories', []))}
+        self.save_fn = save_fn
+        self.verbose = verbose
+        self.history = []            # (epoch, batch, loss) of _train; last validation result in self.val_result
+        self.val_result = None
+        self._val_step = None
+
+    def run_epoches(self):
+        for epoch in range(self.start_epoch, self.end_epoch):
+            self._train(epoch)
+            if self.val_loader:
+                self._val()
+            if self.save_fn is not None:                                   # utils/fit.py:36-41
+                self.save_fn({'model': self.model, 'optimizer': self.optimizer.state_dict()}, 'last.pth')
+        if self.test_loader:
+            self._test()
+
+    def _train(self, epoch):
+        assert self.train_loader, 'train_loader can not be None'
+        self.model.train()
+        for batch_idx, (images, labels) in enumerate(self.train_loader):
+            if self.device.type == 'cuda':
+                images = images.cuda(non_blocking=True)
+                labels = labels.cuda(non_blocking=True)
+            pred = self.model(images)
+            self.optimizer.zero_grad()
+            loss = self.loss(pred, labels)
+            loss.backward()
+            self.optimizer.step()
+            value = loss.item()                                            # the reference reads it every batch (:63)
+            self.history.append((epoch, batch_idx, value))
+            if self.verbose:
+                print("Epoch %d batch %d loss %.6f" % (epoch + 1, batch_idx + 1, value))
+        self.scheduler.step()
+
+    def _model_core(self):
+        return self.model.module if isinstance(self.model, torch.nn.DataParallel) else self.model
+
+    def _val(self):
+        map_est = CalculateMAP(map_iou_values=np.linspace(0.5, 0.95, 10))
+        core = self._model_core()
+        if self._val_step is None:
+            self._val_step = ValStep(core.anchors_per_level, core.backbone_strides_per_level, conf_thres=0.25, iou_thres=0.45,
+                                     max_det=300, ratio_box=self.loss.ratio_box, ratio_conf=self.loss.ratio_conf,
+                                     ratio_cls=self.loss.ratio_cls)
+        step = self._val_step
+        loss_value = None
+        self.model.eval()
+        with torch.no_grad():
+            for batch_idx, (images, labels) in enumerate(self.train_loader):   # (sic: the reference validates on train_loader, :80)
+                if self.device.type == 'cuda':
+                    images = images.cuda(non_blocking=True)
+                    labels = labels.cuda(non_blocking=True)
+                head_out = self.model(images)                              # raw heads; the fused step decodes them itself
+                out = step(head_out, labels)
+                loss_value = out["loss"]
+                # detections of the whole batch as [sum k, 6] = [cls, conf, x1, y1, x2, y2] + CSR offsets (utils/fit.py:94-96)
+                cnt = out["cnt"].long()
+                b, md = cnt.numel(), out["boxes"].size(1)
+                det_off = torch.zeros(b + 1, dtype=torch.int32, device=cnt.device)
+                det_off[1:] = torch.cumsum(cnt, 0)
+                valid = torch.arange(md, device=cnt.device)[None, :] < cnt[:, None]
+                dets = torch.cat([out["cls"].float().unsqueeze(-1), out["scores"].unsqueeze(-1), out["boxes"]], 2)[valid]
+                # targets: xywh (normalised) -> xyxy pixels, grouped by image (:98-99)
+                whwh = torch.tensor([images.size(3), images.size(2), images.size(3), images.size(2)], dtype=labels.dtype,
+                                    device=labels.device)
+                order = torch.argsort(labels[:, 0], stable=True)
+                lab = labels[order]
+                half = lab[:, 4:6] / 2
+                gts = torch.cat([lab[:, 1:2], (lab[:, 2:4] - half), (lab[:, 2:4] + half)], 1)
+                gts[:, 1:] = gts[:, 1:] * whwh
+                gt_off = torch.zeros(b + 1, dtype=torch.int32, device=cnt.device)
+                gt_off[1:] = torch.cumsum(torch.bincount(lab[:, 0].long(), minlength=b)[:b], 0)
+                map_est.process_batch(dets.contiguous(), det_off, gts.contiguous(), gt_off)
+        map_each_iou, map_each_cls, map_each_cls_idx = map_est.fetch()
+        loss_value = float(loss_value) if loss_value is not None else float('nan')
+        self.val_result = (loss_value, map_each_iou, map_each_cls, map_each_cls_idx)
+        if self.verbose:
+            print(f'loss : {loss_value} map : {map_each_iou.tolist()}')
+        return self.val_result
+
+    def _test(self):
+        pass
