@@ -66,7 +66,7 @@ def test_fit_train_matches_cpu_reference_training():
             loss = oracle.loss.yolov3_loss(ref(images), labels, cfg.anchors_levels(), cfg.strides)
             loss.sum().backward()
             ropt.step()
-            want.append(float(loss))
+            want.append(float(loss.detach()))
         rsched.step()
     got = [h[2] for h in fit.history]
     np.testing.assert_allclose(got, want, rtol=2e-5)

@@ -45,6 +45,12 @@ def test_drop_in_names_match_the_reference():
     for name in ["Yolov3Loss", "BiCrossEntropyLoss", "IOULoss", "GIOULoss", "DIOULoss", "CIOULoss"]:
         assert callable(getattr(l, name)), name
     assert callable(m.CalculateMAP)
+    from fastvision_b200.utils import Fit
+    from fastvision_b200.detection.tools import KMeans, AnchorGenerator  # noqa: F401
+    from fastvision_b200.loss import ComputeLoss, ComputeLossU  # noqa: F401
+    import inspect
+    assert list(inspect.signature(Fit.__init__).parameters)[:12] == ['self', 'model', 'device', 'optimizer', 'scheduler', 'loss', 'end_epoch',
+                                                                     'start_epoch', 'train_loader', 'val_loader', 'test_loader', 'data_dict']
 
 
 def test_cpu_tensors_are_rejected_loudly():
