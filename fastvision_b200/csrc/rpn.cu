@@ -123,7 +123,7 @@ namespace cg = cooperative_groups;
 constexpr int kRpnCluster = 2;
 
 struct RpnClusterSmem {
-  size_t cnt, warp_tot, kbox, karea, kslot, gs, xalive, total;
+  size_t cnt, warp_tot, kbox, karea, kslot, gs, xalive, xtot, dig_base, total;
 };
 __host__ __device__ inline RpnClusterSmem rpn_cluster_layout(int max_keep) {
   RpnClusterSmem L;
@@ -142,8 +142,125 @@ __host__ __device__ inline RpnClusterSmem rpn_cluster_layout(int max_keep) {
   L.kslot = take((size_t)local * 4);
   L.gs = take(sizeof(GreedyShared));
   L.xalive = take((size_t)2 * kRpnCluster * 2 * 4);  // [chunk parity][source rank][word]
+  L.xtot = take((size_t)kRpnCluster * 256 * 4);       // per-digit totals of every CTA (cluster sort)
+  L.dig_base = take((size_t)256 * 4);
   L.total = o;
   return L;
+}
+
+// Stable LSD radix sort of the image's n keys by their high 32 bits, split over the CTAs of the cluster: CTA c counts and
+// scatters the c-th contiguous share of the keys (so, for equal digits, CTA 0's keys stay in front of CTA 1's), the
+// per-digit totals travel through distributed shared memory, one cluster barrier after the histograms and one after the
+// scatter.  xtot: [kRpnCluster][256] u32 in every CTA (slot r written by CTA r).  Returns the buffer holding the result.
+__device__ inline unsigned long long* cluster_radix_sort_hi32(cg::cluster_group& cluster, int rank, unsigned long long* src,
+                                                              unsigned long long* dst, int n, uint32_t* cnt, uint32_t* warp_tot,
+                                                              uint32_t* xtot, uint32_t* dig_base) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int share = (((n + kRpnCluster - 1) / kRpnCluster) + 31) & ~31;
+  const int cbeg = min(n, rank * share), cend = min(n, cbeg + share);
+  const int chunk = ((((cend - cbeg) + kNmsWarps - 1) / kNmsWarps) + 31) & ~31;
+  const int beg = min(cend, cbeg + warp * chunk), end = min(cend, beg + chunk);
+  uint32_t* peer_tot[kRpnCluster];
+#pragma unroll
+  for (int r = 0; r < kRpnCluster; ++r) peer_tot[r] = cluster.map_shared_rank(xtot, r);
+  for (int shift = 32; shift < 64; shift += 8) {
+    for (int i = threadIdx.x; i < kNmsWarps * 256; i += kNmsThreads) cnt[i] = 0;
+    __syncthreads();
+    for (int base = beg; base < end; base += 128) {
+      unsigned long long k4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        k4[u] = i < end ? src[i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        const bool act = i < end;
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (act) {
+          const uint32_t d = (uint32_t)(k4[u] >> shift) & 255u;
+          const unsigned peers = __match_any_sync(m, d);
+          if (lane == __ffs(peers) - 1) cnt[d * kNmsWarps + warp] += __popc(peers);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    {
+      constexpr int PER = kNmsWarps * 256 / kNmsThreads;  // 8
+      uint32_t loc[PER], sum = 0;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        loc[k] = cnt[threadIdx.x * PER + k];
+        sum += loc[k];
+      }
+      uint32_t run = block_exclusive_scan(sum, warp_tot);
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        cnt[threadIdx.x * PER + k] = run;
+        run += loc[k];
+      }
+    }
+    __syncthreads();
+    // cnt[d*W + w] = my keys with a smaller digit, or digit d in an earlier warp.  My total of digit d:
+    if (threadIdx.x < 256) {
+      const int d = threadIdx.x;
+      const uint32_t nxt = d < 255 ? cnt[(d + 1) * kNmsWarps] : (uint32_t)(cend - cbeg);
+      const uint32_t tot = nxt - cnt[d * kNmsWarps];
+#pragma unroll
+      for (int r = 0; r < kRpnCluster; ++r) peer_tot[r][rank * 256 + d] = tot;
+    }
+    cluster.sync();
+    // global start of digit d = keys of all CTAs with a smaller digit (+ digit d of the CTAs before me)
+    {
+      uint32_t all = 0, before = 0;
+      if (threadIdx.x < 256) {
+#pragma unroll
+        for (int r = 0; r < kRpnCluster; ++r) {
+          const uint32_t t = xtot[r * 256 + threadIdx.x];
+          all += t;
+          if (r < rank) before += t;
+        }
+      }
+      const uint32_t excl = block_exclusive_scan(all, warp_tot);
+      if (threadIdx.x < 256) dig_base[threadIdx.x] = excl + before - cnt[threadIdx.x * kNmsWarps];
+    }
+    __syncthreads();
+    for (int base = beg; base < end; base += 128) {
+      unsigned long long k4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        k4[u] = i < end ? src[i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + 32 * u + lane;
+        const bool act = i < end;
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        uint32_t d = 0;
+        unsigned peers = 0;
+        if (act) {
+          const unsigned long long key = k4[u];
+          d = (uint32_t)(key >> shift) & 255u;
+          peers = __match_any_sync(m, d);
+          const uint32_t pos = dig_base[d] + cnt[d * kNmsWarps + warp] + __popc(peers & lt_mask);
+          dst[pos] = key;
+        }
+        __syncwarp();
+        if (act && lane == __ffs(peers) - 1) cnt[d * kNmsWarps + warp] += __popc(peers);
+        __syncwarp();
+      }
+    }
+    __threadfence();
+    cluster.sync();  // dst is complete (both shares) before anybody reads it as the next pass's source
+    unsigned long long* t = src;
+    src = dst;
+    dst = t;
+  }
+  return src;
 }
 
 __global__ void __cluster_dims__(kRpnCluster, 1, 1) __launch_bounds__(kNmsThreads) rpn_nms_cluster_kernel(const RpnParams p) {
@@ -162,15 +279,9 @@ __global__ void __cluster_dims__(kRpnCluster, 1, 1) __launch_bounds__(kNmsThread
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
   unsigned long long* keys0 = p.keys + (size_t)b * 2 * p.n;
   const float4* box = p.box + (size_t)b * p.n;
-  // the sort is one CTA's job (both buffers of the image are shared); its result is published by the cluster barrier
-  __shared__ const unsigned long long* s_sorted;
-  if (rank == 0) {
-    const unsigned long long* srt = block_radix_sort_hi32(keys0, keys0 + p.n, p.n, cnt, warp_tot);
-    if (tid == 0) s_sorted = srt;
-  }
-  __threadfence();
-  cluster.sync();
-  const unsigned long long* sorted = *cluster.map_shared_rank(&s_sorted, 0);
+  uint32_t* xtot = reinterpret_cast<uint32_t*>(smem + L.xtot);
+  uint32_t* dig_base = reinterpret_cast<uint32_t*>(smem + L.dig_base);
+  const unsigned long long* sorted = cluster_radix_sort_hi32(cluster, rank, keys0, keys0 + p.n, p.n, cnt, warp_tot, xtot, dig_base);
   const int n = min(p.pre_n, p.n);  // rpn.py:193-195 topk
   const int max_keep = p.post_n;
   const float thr = p.iou_thr;
@@ -376,8 +487,8 @@ extern "C" int fvb_rpn_proposals_f32(const float* d_cls, const float* d_reg, con
   dim3 grid((unsigned)((n + 255) / 256), (unsigned)batch);
   rpn_decode_kernel<<<grid, 256, 0, cs>>>(p);
   count_launch();
-  // long greedy passes (many candidates, many proposals kept) run on a 2-CTA cluster per image; FVB_RPN_CLUSTER=0/1 overrides
-  bool use_cluster = (pre_n < n ? pre_n : n) >= 4096 && p.post_n >= 1024;
+  // images with many anchors (sort + greedy both long) run on a 2-CTA cluster per image; FVB_RPN_CLUSTER=0/1 overrides
+  bool use_cluster = n >= 4096;
   if (const char* e = getenv("FVB_RPN_CLUSTER")) use_cluster = e[0] == '1';
   if (use_cluster) {
     RpnClusterSmem LC = rpn_cluster_layout(p.post_n);
