@@ -6,7 +6,7 @@
 // publish my partials into slot e&1 of MY buffer, release-store flag = e, acquire-spin on every peer's flag, then every rank
 // sums the W vectors in rank order -- bit-identical results on all ranks -- and forms the loss with the global-batch
 // normalisers.  Slot reuse is safe: a rank reaches epoch e+2 only after all peers published e+1, i.e. finished reading e.
-// A peer that never arrives trips a ~2 s timeout: status := 1, loss := NaN (no hang).
+// A peer that never arrives trips a ~10 s timeout: status := 1, loss := NaN (no hang).
 #include "common.cuh"
 
 namespace fvb {
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(32) peer_reduce_combine_kernel(const PeerParam
     const PeerBuf* pb = reinterpret_cast<const PeerBuf*>(p.peers[tid]);
     const long long t0 = clock64();
     while (ld_acquire_sys(&pb->slot[s].flag) < e) {
-      if (clock64() - t0 > 4000000000ll) {  // ~2 s: a rank is missing -- give up instead of hanging the GPU
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a rank is missing -- give up instead of hanging the GPU
         ok = false;
         break;
       }

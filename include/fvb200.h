@@ -220,7 +220,7 @@ int fvb_yolov3_loss_combine_f32(const fvb_yolo_geom* geom, int64_t batch_global,
  * d_peer_ptrs: device array [world] of the base addresses of every rank's peer buffer (fvb_peer_buffer_bytes() bytes, ZEROED
  * once before first use, mapped into this process -- torch symmetric memory provides them).  Every rank must make the same
  * sequence of calls on one buffer set.  d_partials_out [L*4] receives the global sums (same bits on all ranks), d_out_loss the
- * scalar; d_status (may be NULL) 0, or 1 if a peer did not arrive within ~2 s (loss := NaN, no hang). */
+ * scalar; d_status (may be NULL) 0, or 1 if a peer did not arrive within ~10 s (loss := NaN, no hang). */
 size_t fvb_peer_buffer_bytes(void);
 int fvb_yolov3_loss_peer_combine_f32(const fvb_yolo_geom* geom, int64_t batch_global, const double* d_partials,
                                      const uint64_t* d_peer_ptrs, int rank, int world, float ratio_box, float ratio_conf,
