@@ -481,3 +481,50 @@ def test_decode_nchw_heads(cfg, batch):
     got_yxa = yolov3_decode([h.cuda() for h in nchw], anc, st, layout="nchw", row_order="yxa")
     close(got_yxa, oracle.decode.decode_demo_nchw(nchw, anc_feat, st, order="yxa"))
 
+
+
+def test_full_size_properties_config3_ship608():
+    """BASELINE configs[2] at its 8-GPU per-rank share (YOLOv3-608, 10 classes, 128 images, K = 15 channels -- the narrow-row
+    decode path, ~1400 NMS candidates per image): batch independence, oracle spot checks of decode / NMS / loss, NMS invariants,
+    and the sharded loss (4 ranks' partials) against the full batch."""
+    cfg, batch = synth.SHIP608, 128
+    g = synth.make_generator(3)
+    labels = synth.make_labels(cfg, batch, g)
+    heads = synth.make_heads(cfg, batch, labels, g)
+    step = ValStep(cfg.anchors_levels(), cfg.strides)
+    dh, dl = [h.cuda() for h in heads], labels.cuda()
+    out = {k: v.clone() for k, v in step(dh, dl).items()}
+    sub = ValStep(cfg.anchors_levels(), cfg.strides)
+    o4 = sub([h[60:64].contiguous() for h in dh], shard_labels(dl, 60, 64))
+    assert torch.equal(o4["results"], out["results"][60:64]) and torch.equal(o4["cnt"], out["cnt"][60:64])
+    for i in range(4):
+        k = int(o4["cnt"][i])
+        assert torch.equal(o4["boxes"][i, :k], out["boxes"][60 + i, :k])
+    pick = [0, 63, 127]
+    want_res = oracle.decode.decode([h[pick] for h in heads], cfg.anchors_levels(), cfg.strides)
+    close(out["results"][pick], want_res)
+    res_cpu = out["results"][pick].cpu()
+    for j, i in enumerate(pick):
+        ws, wc, wb = on.nms_lib(res_cpu[j], 0.25, 0.45, 300)
+        k = int(out["cnt"][i])
+        assert k == ws.size(0)
+        assert np.array_equal(out["boxes"][i, :k].cpu().numpy(), wb.numpy())
+        assert np.array_equal(out["cls"][i, :k].cpu().numpy(), wc.view(-1).numpy())
+    for i in range(0, batch, 13):
+        k = int(out["cnt"][i])
+        s = out["scores"][i, :k]
+        assert bool((s[:-1] >= s[1:]).all())
+        iou = ft.cal_iou_batch(out["boxes"][i, :k].contiguous(), out["boxes"][i, :k].contiguous())
+        iou.fill_diagonal_(0)
+        assert float(iou.max()) <= 0.45 + 1e-6
+    sl = slice(0, 16)
+    sub_labels = shard_labels(labels, 0, 16)
+    want_loss = ol.yolov3_loss([h[sl] for h in heads], sub_labels, cfg.anchors_levels(), cfg.strides)
+    lossf = fl.Yolov3Loss(_Model(cfg), 0.5, 0.05, 1.0, 0.5)
+    close(lossf([h[sl].contiguous() for h in dh], sub_labels.cuda()), want_loss)
+    p = torch.zeros(3, 4, dtype=torch.float64, device="cuda")
+    for lo in range(0, batch, 32):
+        lossf([h[lo:lo + 32].contiguous() for h in dh], shard_labels(dl, lo, lo + 32))
+        p += lossf.partials
+    close(p, out["partials"], rtol=1e-9, atol=0)
+    close(lossf.combine(p, batch, ctx=step.ctx), out["loss"])
