@@ -56,51 +56,54 @@ class KMeans():
 
 
 class AnchorGenerator():
+    """Same constructor and ``get_anchors()`` result as ANCHOR.py:50-120: collects the normalised (w, h) of every label the data
+    loaders yield, clusters them on the device, orders the centres by decreasing area and scales them to the input size.  The
+    cache file keeps the reference's format (``str`` of a nested list in ``<cache>/anchor.txt``)."""
+
     def __init__(self, data_loaders: list, k=9, iters=100, num_workers=1, plot=True, cache='./cache', use_cache=False):
-        self.data_loaders = data_loaders
-        self.k = k
-        self.iters = iters
-        self.num_workers = num_workers
+        self.data_loaders, self.k, self.iters, self.num_workers = data_loaders, k, iters, num_workers
+        self.cache_dir = cache
         self.cache = os.path.join(cache, 'anchor.txt')
-        self.use_cache = use_cache
-        self.plot = plot
+        self.use_cache, self.plot = use_cache, plot
+        self.input_height = self.input_widht = None          # (attribute spelled as in the reference, ANCHOR.py:77)
 
     def load_data(self):
-        wh_normal = []
+        """[sum T, 2] float array of label (w, h); remembers the input size of the last batch seen (ANCHOR.py:62-86)."""
+        chunks = []
         for loader in self.data_loaders:
-            for (images, labels) in loader:                                  # ANCHOR.py:76-78
-                self.input_height, self.input_widht = images.size()[2:]
-                wh_normal.append(labels[:, 4:].cpu().numpy())
-        return np.concatenate(wh_normal, axis=0)
+            for images, labels in loader:
+                self.input_height, self.input_widht = int(images.shape[2]), int(images.shape[3])
+                chunks.append(labels[:, 4:].detach().cpu().numpy())
+        return np.concatenate(chunks, axis=0)
 
     def load_cache(self):
-        with open(self.cache, 'r') as f:
-            centers = eval(f.read())
-        return centers
+        import ast
+        with open(self.cache) as fh:
+            return ast.literal_eval(fh.read())
+
+    def _plot(self, wh, categories, centers):
+        try:
+            from matplotlib import pyplot as plt
+        except ImportError:
+            return
+        for cid in range(1, self.k + 1):
+            sel = categories == cid
+            plt.scatter(wh[sel, 0], wh[sel, 1], alpha=0.8)
+        plt.scatter(centers[:, 0], centers[:, 1], c='black', marker='x')
+        plt.savefig(os.path.join(self.cache_dir, 'anchor.png'))
 
     def get_anchors(self):
         if self.use_cache:
-            centers = self.load_cache()
             print(f'Use anchor from cache {self.cache}')
-            return np.array(centers, dtype=float).reshape([-1, 2])
-        wh_normal = self.load_data()
-        wh_normal = np.array(wh_normal, dtype=np.float32).reshape([-1, 2])
-        centers, categories = KMeans(xs=wh_normal, k=self.k).fit(iters=self.iters)
-        centers = centers.tolist()
-        centers.sort(key=lambda x: -x[0] * x[1])                            # ANCHOR.py:106
-        centers = np.array(centers, dtype=float).reshape([-1, 2])
+            return np.asarray(self.load_cache(), dtype=float).reshape(-1, 2)
+        wh = np.asarray(self.load_data(), dtype=np.float32).reshape(-1, 2)
+        centers, categories = KMeans(xs=wh, k=self.k).fit(iters=self.iters)
+        order = sorted(range(len(centers)), key=lambda i: -float(centers[i][0]) * float(centers[i][1]))   # ANCHOR.py:106, stable
+        centers = np.asarray([centers[i].tolist() for i in order], dtype=float).reshape(-1, 2)
+        os.makedirs(self.cache_dir, exist_ok=True)
         if self.plot:
-            try:
-                from matplotlib import pyplot as plt
-                for k in range(1, self.k + 1):
-                    plt.scatter(wh_normal[categories == k, 0], wh_normal[categories == k, 1], alpha=0.8)
-                    plt.scatter(centers[:, 0], centers[:, 1], c='black', marker='x')
-                os.makedirs(os.path.dirname(self.cache) or '.', exist_ok=True)
-                plt.savefig(os.path.join(os.path.dirname(self.cache) or '.', 'anchor.png'))
-            except ImportError:
-                pass
-        centers = centers * np.array([self.input_widht, self.input_height])  # :116
-        os.makedirs(os.path.dirname(self.cache) or '.', exist_ok=True)
-        with open(self.cache, 'w') as f:
-            f.write(str(centers.tolist()))
-        return centers
+            self._plot(wh, categories, centers)
+        pixels = centers * np.array([self.input_widht, self.input_height])                                 # ANCHOR.py:116
+        with open(self.cache, 'w') as fh:
+            fh.write(str(pixels.tolist()))
+        return pixels

@@ -36,31 +36,38 @@ class Fit():
         self._val_step = None
 
     def run_epoches(self):
-        for epoch in range(self.start_epoch, self.end_epoch):
+        """utils/fit.py:28-45: train every epoch, validate when a val_loader is given, checkpoint through ``save_fn``."""
+        epoch = self.start_epoch
+        while epoch < self.end_epoch:
             self._train(epoch)
             if self.val_loader:
                 self._val()
-            if self.save_fn is not None:                                   # utils/fit.py:36-41
+            if self.save_fn is not None:
                 self.save_fn({'model': self.model, 'optimizer': self.optimizer.state_dict()}, 'last.pth')
+            epoch += 1
         if self.test_loader:
             self._test()
 
+    def _to_device(self, *tensors):
+        if self.device.type != 'cuda':
+            return tensors
+        return tuple(t.cuda(non_blocking=True) for t in tensors)
+
     def _train(self, epoch):
+        """utils/fit.py:47-71: forward, zero_grad, loss, backward, step; the scheduler advances once per epoch."""
         assert self.train_loader, 'train_loader can not be None'
         self.model.train()
-        for batch_idx, (images, labels) in enumerate(self.train_loader):
-            if self.device.type == 'cuda':
-                images = images.cuda(non_blocking=True)
-                labels = labels.cuda(non_blocking=True)
-            pred = self.model(images)
+        for step_no, batch in enumerate(self.train_loader):
+            images, labels = self._to_device(*batch)
+            outputs = self.model(images)
             self.optimizer.zero_grad()
-            loss = self.loss(pred, labels)
-            loss.backward()
+            loss = self.loss(outputs, labels)
+            loss.backward()                                   # CUDA backward kernels (fvb_yolov3_loss_backward_f32)
             self.optimizer.step()
-            value = loss.item()                                            # the reference reads it every batch (:63)
-            self.history.append((epoch, batch_idx, value))
+            scalar = loss.item()                              # the reference reads the loss every batch too (:63)
+            self.history.append((epoch, step_no, scalar))
             if self.verbose:
-                print("Epoch %d batch %d loss %.6f" % (epoch + 1, batch_idx + 1, value))
+                print("Epoch %d batch %d loss %.6f" % (epoch + 1, step_no + 1, scalar))
         self.scheduler.step()
 
     def _model_core(self):
@@ -77,10 +84,8 @@ class Fit():
         loss_value = None
         self.model.eval()
         with torch.no_grad():
-            for batch_idx, (images, labels) in enumerate(self.train_loader):   # (sic: the reference validates on train_loader, :80)
-                if self.device.type == 'cuda':
-                    images = images.cuda(non_blocking=True)
-                    labels = labels.cuda(non_blocking=True)
+            for batch in self.train_loader:                                # (sic: the reference validates on train_loader, :80)
+                images, labels = self._to_device(*batch)
                 head_out = self.model(images)                              # raw heads; the fused step decodes them itself
                 out = step(head_out, labels)
                 loss_value = out["loss"]
