@@ -8,11 +8,11 @@
 //   1  one thread per candidate: load its 32-byte record {x,y,w,h,conf,max_c(cls*conf),argmax}
 //      (written by the decode kernel while the row was in registers, or by yolo_score_kernel when
 //      NMS is called on its own), xywh->xyxy, optional class gap (box + cat*max_wh in fp32);
-//   2  block radix sort of (rank desc, slot asc) keys;
+//   2  block sort of (rank desc, slot asc) keys: bitonic network in registers/shared memory up to kCapS keys, LSD radix beyond;
 //   3  chunked greedy suppression with a kept list (nms.cuh);
 //   4  padded outputs + count; consumed bitmap words are cleared for the next step.
-// Candidates live in shared memory up to kCapS per image (keys, boxes, rows: 36 B each -- under 100 KB per CTA so
-// that TWO CTAs fit an SM and 256 images are one wave); beyond that the same code runs on a global workspace
+// Candidates live in shared memory up to kCapS per image (keys, boxes, rows: 28 B each -- 82 KB per CTA so
+// that TWO CTAs fit an SM and 256 images are one wave; sorted there with the in-register bitonic network of nms.cuh); beyond that the same code runs on a global workspace
 // slice (slower, still exact) so there is no overflow case.
 #include "nms.cuh"
 
@@ -52,7 +52,7 @@ struct YoloNmsParams {
 };
 
 struct NmsSmemLayout {
-  size_t keys0, keys1, box, row, cnt, warp_tot, kbox, karea, kslot, gs, misc, total;
+  size_t keys0, box, row, cnt, warp_tot, kbox, karea, kslot, gs, misc, total;
 };
 
 __host__ __device__ inline NmsSmemLayout nms_layout(int cap, int max_keep) {
@@ -64,8 +64,7 @@ __host__ __device__ inline NmsSmemLayout nms_layout(int cap, int max_keep) {
     o += bytes;
     return r;
   };
-  L.keys0 = take((size_t)cap * 8, 16);
-  L.keys1 = take((size_t)cap * 8, 16);
+  L.keys0 = take((size_t)cap * 8, 16);  // sorted in place (bitonic); the radix sort's second buffer exists only in the global fallback
   L.box = take((size_t)cap * 16, 16);
   L.row = take((size_t)cap * 4, 16);
   L.cnt = take((size_t)kNmsWarps * 256 * 4, 16);
@@ -109,7 +108,7 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
   int* srow;
   if (n <= kCapS) {
     keys0 = reinterpret_cast<unsigned long long*>(smem + L.keys0);
-    keys1 = reinterpret_cast<unsigned long long*>(smem + L.keys1);
+    keys1 = nullptr;
     sbox = reinterpret_cast<float4*>(smem + L.box);
     srow = reinterpret_cast<int*>(smem + L.row);
   } else {
@@ -173,7 +172,11 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
 
   // ---- phase 2 + 3 ---------------------------------------------------------------------------------------
   if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 2] = gtime_ns();
-  unsigned long long* sorted = block_radix_sort_hi32(keys0, keys1, n, cnt, warp_tot);
+  unsigned long long* sorted = keys0;
+  if (n <= kCapS)
+    block_bitonic_sort64(keys0, n);
+  else
+    sorted = block_radix_sort_hi32(keys0, keys1, n, cnt, warp_tot);
   if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 3] = gtime_ns();
   int kept = block_greedy_nms(sorted, n_use, sbox, p.iou_thr, p.max_det, kbox, karea, kslot, gs);
   if (p.trace && threadIdx.x == 0) { p.trace[b * 8 + 4] = gtime_ns(); p.trace[b * 8 + 6] = n; p.trace[b * 8 + 7] = kept; }
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(kNmsThreads) seg_nms_kernel(const SegNmsParams
   float4* sbox;
   if (n <= kCapS) {
     keys0 = reinterpret_cast<unsigned long long*>(smem + L.keys0);
-    keys1 = reinterpret_cast<unsigned long long*>(smem + L.keys1);
+    keys1 = nullptr;
     sbox = reinterpret_cast<float4*>(smem + L.box);
   } else {
     keys0 = p.ws_keys + (size_t)2 * beg;
@@ -301,7 +304,11 @@ __global__ void __launch_bounds__(kNmsThreads) seg_nms_kernel(const SegNmsParams
     keys0[i] = ((unsigned long long)desc_key(p.scores[beg + i]) << 32) | (uint32_t)i;
   }
   __syncthreads();
-  unsigned long long* sorted = block_radix_sort_hi32(keys0, keys1, n, cnt, warp_tot);
+  unsigned long long* sorted = keys0;
+  if (n <= kCapS)
+    block_bitonic_sort64(keys0, n);
+  else
+    sorted = block_radix_sort_hi32(keys0, keys1, n, cnt, warp_tot);
   int kept = block_greedy_nms(sorted, n, sbox, p.iou_thr, p.max_keep, kbox, karea, kslot, gs);
   for (int i = threadIdx.x; i < kept; i += kNmsThreads) p.keep_idx[(size_t)s * p.max_keep + i] = kslot[i];
   if (threadIdx.x == 0) p.keep_cnt[s] = kept;
