@@ -11,7 +11,7 @@ from fastvision_b200.detection.models import yolov3_decode, DecodeContext  # noq
 from fastvision_b200.detection.tools import non_max_suppression_batched  # noqa: E402
 
 cfg = synth.COCO416
-B = 256
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 g = synth.make_generator(2)
 labels = synth.make_labels(cfg, B, g)
 heads = [h.cuda() for h in synth.make_heads(cfg, B, labels, g)]
