@@ -210,6 +210,24 @@ def test_nms_segmented_batched_and_large():
         assert np.array_equal(got, want), (i, n)
 
 
+def test_nms_segmented_sort_boundaries_and_score_ties():
+    """Every size class of the in-kernel sort (bitonic network: 64..1024 keys at 2 per thread, 2048 at 4 per thread; radix
+    beyond) with scores drawn from a handful of values, so the order is decided by the tie rule (lower index first)."""
+    gen = torch.Generator().manual_seed(91)
+    sizes = [1, 2, 63, 64, 65, 127, 128, 129, 511, 512, 513, 1023, 1024, 1025, 1400, 2047, 2048, 2049]
+    boxes, scores = [], []
+    for n in sizes:
+        xy = torch.rand(n, 2, generator=gen) * 300
+        boxes.append(torch.cat([xy, xy + torch.rand(n, 2, generator=gen) * 30 + 1], 1))
+        scores.append(torch.randint(0, 7, (n,), generator=gen).float() / 8 + 0.125)
+    off = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32)
+    keep, cnt = ft.nms(torch.cat(boxes).cuda(), torch.cat(scores).cuda(), 0.5, seg_offsets=off.cuda(), max_keep=2049)
+    for i, n in enumerate(sizes):
+        want = on.nms_greedy(boxes[i], scores[i], 0.5).numpy()
+        got = keep[i, :int(cnt[i])].cpu().numpy()
+        assert np.array_equal(got, want), (i, n)
+
+
 def test_nms_batched_config1_exact_on_same_decoded_tensor():
     cfg, batch = synth.COCO416, 8
     g = synth.make_generator(1)
