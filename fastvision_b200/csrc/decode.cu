@@ -17,7 +17,9 @@
 //         bitmap; candidate rows (~7 %) get their 32-byte NMS record from the class scores sitting in shared memory;
 //   * the finished tile is copied out flat: every store instruction writes 128 contiguous bytes (512 when the
 //     destination run is 16-byte aligned).
-// The kernel keeps <= 113 KB of shared memory per SM so that one NMS CTA can be co-resident (pipeline.py).
+// The kernel keeps <= 113 KB of shared memory per SM and, through its launch bound, <= 64 registers per thread (58 used, no
+// spills; 640 threads -> 40 960 registers) so that one NMS CTA (512 threads x 40 registers, 82 KB) can be co-resident
+// (pipeline.py: the NMS tail of batch i under the decode of batch i+1).
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -25,7 +27,7 @@
 namespace fvb {
 
 constexpr int kDecodeWarps = kDecodeThreads / 32;  // default warps per CTA
-constexpr int kDecodeMaxThreads = 768;
+constexpr int kDecodeMaxThreads = 1024;  // launch bound: caps the kernel at 64 registers per thread
 
 struct DecodeParams {
   Geom g;
