@@ -27,6 +27,7 @@
 namespace fvb {
 
 constexpr int kDecodeWarps = kDecodeThreads / 32;  // default warps per CTA
+constexpr int kLaneRowClasses = 32;   // up to this many classes a candidate's record is built by its own lane (process_tile B1)
 constexpr int kDecodeMaxThreads = 1024;  // launch bound: caps the kernel at 64 registers per thread
 
 struct DecodeParams {
@@ -304,7 +305,27 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
         }
       }
       // candidate records: score = max_c(cls_c*conf) on the STORED fp32 values (NMS.py:13,16: first maximum on ties)
-      if (p.cand_rec != nullptr) {
+      if (p.cand_rec != nullptr && K - 5 <= kLaneRowClasses) {
+        // few classes (K = 15: a candidate every 16 rows, several per 32-row group): every candidate lane walks its OWN row's
+        // class scores -- the candidates of a group in parallel, one 32-byte record store per lane -- instead of the warp
+        // taking them one after the other (measured at 608 / C=10 / B=1024: 740 cycles per candidate, decode 0.46 -> 0.65 ms)
+        if (valid && conf[sb] > p.conf_thr) {
+          const float* cls = buf + r * K + 5;
+          const float rconf = conf[sb];
+          unsigned best = __float_as_uint(cls[0] * rconf);
+          int bidx = 0;
+          for (int c = 1; c < K - 5; ++c) {
+            const unsigned pr = __float_as_uint(cls[c] * rconf);
+            if (pr > best) {  // strict >: the first maximum wins
+              best = pr;
+              bidx = c;
+            }
+          }
+          float4* rec = reinterpret_cast<float4*>(p.cand_rec + (t.out_row + r) * 8);
+          rec[0] = make_float4(ox[sb], oy[sb], ow[sb], oh[sb]);
+          rec[1] = make_float4(rconf, __uint_as_float(best), __int_as_float(bidx), 0.0f);
+        }
+      } else if (p.cand_rec != nullptr) {
         while (m) {
           const int rr = __ffs(m) - 1;
           m &= m - 1;
@@ -589,6 +610,7 @@ extern "C" int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const
   }
   FVB_REQUIRE((reinterpret_cast<uintptr_t>(d_results) & 3) == 0 && (reinterpret_cast<uintptr_t>(d_ws) & 7) == 0, "decode: results / workspace misaligned");
   FVB_REQUIRE(d_cand_rec == nullptr || d_cand_bitmap != nullptr, "decode: candidate records need the candidate bitmap too");
+  FVB_REQUIRE(((uintptr_t)d_cand_rec & 15) == 0, "decode: candidate records must be 16-byte aligned");
   if (p.g.B == 0) return FVB_OK;
   DecodeShape sh;
   rc = decode_launch_shape(p.g, &sh);

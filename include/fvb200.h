@@ -94,7 +94,7 @@ typedef struct {
  *   d_cand_bitmap  [B, fvb_yolo_bitmap_words(geom)] u32, must be zero on entry: bit r of image b
  *                  is set iff results[b,r,4] > conf_thr -- the candidate set of
  *                  non_max_suppression (detection/tools/NMS.py:7-8) without a second pass;
- *   d_cand_rec     [B, N, 8] f32 (needs d_cand_bitmap): for every candidate row r the record
+ *   d_cand_rec     [B, N, 8] f32, 16-byte aligned (needs d_cand_bitmap): for every candidate row r the record
  *                  {results[b,r,0..3], conf, max_c(cls_c*conf), argmax_c as int bits, unused} -- what
  *                  NMS.py:13-16 computes per candidate, produced while the row is in registers so the
  *                  NMS kernel never re-reads the 4*K-byte rows; non-candidate records are not written;
