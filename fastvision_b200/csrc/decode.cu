@@ -305,27 +305,7 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
         }
       }
       // candidate records: score = max_c(cls_c*conf) on the STORED fp32 values (NMS.py:13,16: first maximum on ties)
-      if (p.cand_rec != nullptr && K - 5 <= kLaneRowClasses) {
-        // few classes (K = 15: a candidate every 16 rows, several per 32-row group): every candidate lane walks its OWN row's
-        // class scores -- the candidates of a group in parallel, one 32-byte record store per lane -- instead of the warp
-        // taking them one after the other (measured at 608 / C=10 / B=1024: 740 cycles per candidate, decode 0.46 -> 0.65 ms)
-        if (valid && conf[sb] > p.conf_thr) {
-          const float* cls = buf + r * K + 5;
-          const float rconf = conf[sb];
-          unsigned best = __float_as_uint(cls[0] * rconf);
-          int bidx = 0;
-          for (int c = 1; c < K - 5; ++c) {
-            const unsigned pr = __float_as_uint(cls[c] * rconf);
-            if (pr > best) {  // strict >: the first maximum wins
-              best = pr;
-              bidx = c;
-            }
-          }
-          float4* rec = reinterpret_cast<float4*>(p.cand_rec + (t.out_row + r) * 8);
-          rec[0] = make_float4(ox[sb], oy[sb], ow[sb], oh[sb]);
-          rec[1] = make_float4(rconf, __uint_as_float(best), __int_as_float(bidx), 0.0f);
-        }
-      } else if (p.cand_rec != nullptr) {
+      if (p.cand_rec != nullptr && K - 5 > kLaneRowClasses) {
         while (m) {
           const int rr = __ffs(m) - 1;
           m &= m - 1;
@@ -348,6 +328,47 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
             const float val = lane < 5 ? row[lane] : (lane == 5 ? __uint_as_float(wbest) : __int_as_float(widx));
             p.cand_rec[(t.out_row + sb * 32 + rr) * 8 + lane] = val;
           }
+        }
+      }
+    }
+  }
+  // few classes (K = 15: a candidate every 16 rows, several per 32-row group): every candidate lane walks its OWN rows' class
+  // scores -- all candidates of the tile in parallel, the NSB rows of a lane as independent chains, one 32-byte record
+  // store per candidate -- instead of the warp taking the candidates one after the other (measured at 608 / C=10 / B=1024:
+  // 740 cycles per candidate, decode 0.46 -> 0.65 ms).  Same arithmetic and tie rule (first maximum) as the loop above.
+  if (p.cand_rec != nullptr && K - 5 <= kLaneRowClasses) {
+    bool cand[NSB];
+    bool any = false;
+#pragma unroll
+    for (int sb = 0; sb < NSB; ++sb) {
+      cand[sb] = (sb * 32 + lane < t.nrows) && conf[sb] > p.conf_thr;
+      any |= cand[sb];
+    }
+    if (any) {
+      unsigned best[NSB];
+      int bidx[NSB];
+      const float* cls = buf + lane * K + 5;
+#pragma unroll
+      for (int sb = 0; sb < NSB; ++sb) {
+        best[sb] = __float_as_uint(cls[sb * 32 * K] * conf[sb]);
+        bidx[sb] = 0;
+      }
+      for (int c = 1; c < K - 5; ++c) {
+#pragma unroll
+        for (int sb = 0; sb < NSB; ++sb) {  // rows past the tile's end read stale floats of the buffer; never stored
+          const unsigned pr = __float_as_uint(cls[sb * 32 * K + c] * conf[sb]);
+          if (pr > best[sb]) {  // strict >: the first maximum wins
+            best[sb] = pr;
+            bidx[sb] = c;
+          }
+        }
+      }
+#pragma unroll
+      for (int sb = 0; sb < NSB; ++sb) {
+        if (cand[sb]) {
+          float4* rec = reinterpret_cast<float4*>(p.cand_rec + (t.out_row + sb * 32 + lane) * 8);
+          rec[0] = make_float4(ox[sb], oy[sb], ow[sb], oh[sb]);
+          rec[1] = make_float4(conf[sb], __uint_as_float(best[sb]), __int_as_float(bidx[sb]), 0.0f);
         }
       }
     }
@@ -491,7 +512,9 @@ int decode_launch_shape(const Geom& g, DecodeShape* s) {
   s->stages = 1;
   const size_t per_warp = (size_t)s->tile_floats * sizeof(float);
   int wpc = (int)(kDecodeSmemBudget / per_warp);
-  const int want = knob("FVB_DECODE_WARPS", kDecodeWarps, 1, kDecodeMaxThreads / 32);
+  // narrow rows (K <= 21: 64-128 rows, < 8 KB per tile) carry more per-row work per byte: 24 warps hide it better (608 / C=10 /
+  // B=1024 with all side outputs: 0.557 ms at 20 warps, 0.512 at 24, 0.508 at 28); wide rows are best at 20 (0.304 vs 0.306 ms)
+  const int want = knob("FVB_DECODE_WARPS", s->tile_rows >= 64 ? 24 : kDecodeWarps, 1, kDecodeMaxThreads / 32);
   if (wpc > want) wpc = want;
   if (wpc < 1) {
     set_error("decode: K=%d rows do not fit the shared-memory tile", g.K);
