@@ -281,6 +281,15 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
   __syncwarp();
 
   // ---- B1: head channels back into the tile, candidate bitmap + records ---------------------------------------------
+  // Records: the warp-serial walk costs ~100 instructions per candidate, the lane-per-row walk ~(3 + 3 NSB) per class
+  // whatever the number of candidates: few classes, or a candidate-dense tile (low thresholds), take the latter.
+  bool lane_rows = K - 5 <= kLaneRowClasses;
+  if (p.cand_rec != nullptr && !lane_rows) {
+    int nc = 0;
+#pragma unroll
+    for (int sb = 0; sb < NSB; ++sb) nc += __popc(__ballot_sync(0xffffffffu, sb * 32 + lane < t.nrows && conf[sb] > p.conf_thr));
+    lane_rows = nc * 100 > (K - 5) * (3 + 3 * NSB);
+  }
 #pragma unroll
   for (int sb = 0; sb < NSB; ++sb) {
     const int r = sb * 32 + lane;
@@ -305,7 +314,7 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
         }
       }
       // candidate records: score = max_c(cls_c*conf) on the STORED fp32 values (NMS.py:13,16: first maximum on ties)
-      if (p.cand_rec != nullptr && K - 5 > kLaneRowClasses) {
+      if (p.cand_rec != nullptr && !lane_rows) {
         while (m) {
           const int rr = __ffs(m) - 1;
           m &= m - 1;
@@ -332,11 +341,11 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
       }
     }
   }
-  // few classes (K = 15: a candidate every 16 rows, several per 32-row group): every candidate lane walks its OWN rows' class
+  // few classes (K = 15: a candidate every 16 rows, several per 32-row group) or a dense tile: every candidate lane walks its OWN rows' class
   // scores -- all candidates of the tile in parallel, the NSB rows of a lane as independent chains, one 32-byte record
   // store per candidate -- instead of the warp taking the candidates one after the other (measured at 608 / C=10 / B=1024:
   // 740 cycles per candidate, decode 0.46 -> 0.65 ms).  Same arithmetic and tie rule (first maximum) as the loop above.
-  if (p.cand_rec != nullptr && K - 5 <= kLaneRowClasses) {
+  if (p.cand_rec != nullptr && lane_rows) {
     bool cand[NSB];
     bool any = false;
 #pragma unroll

@@ -60,11 +60,15 @@ def test_decode_nonsquare_odd_shapes():
     close(got, want)
 
 
-def test_decode_fused_side_outputs():
-    cfg, batch = synth.COCO416, 4
+@pytest.mark.parametrize("cfg,stress", [(synth.COCO416, False), (synth.COCO416, True), (synth.SHIP608, False), (synth.SHIP608, True), (SMALL, True)],
+                         ids=["coco416", "coco416-dense", "ship608", "ship608-dense", "tiny-dense"])
+def test_decode_fused_side_outputs(cfg, stress):
+    # the records have two code paths (warp-serial for sparse tiles with many classes, lane-per-row for few classes or
+    # candidate-dense tiles): the dense variants (objectness ~N(0,1)) and the 10- / 4-class configurations cover the second
+    batch = 4 if cfg is not synth.SHIP608 else 2
     g = synth.make_generator(1)
     labels = synth.make_labels(cfg, batch, g)
-    heads = [h.cuda() for h in synth.make_heads(cfg, batch, labels, g)]
+    heads = [h.cuda() for h in synth.make_heads(cfg, batch, labels, g, stress=stress)]
     ctx = DecodeContext(heads, cfg.anchors_levels(), cfg.strides)
     res = yolov3_decode(heads, cfg.anchors_levels(), cfg.strides, ctx=ctx, conf_thres=0.25, want_bce0=True)
     # bitmap == (conf > thr) on the values the kernel itself stored
