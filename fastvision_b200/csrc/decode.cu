@@ -356,16 +356,17 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
     if (any) {
       unsigned best[NSB];
       int bidx[NSB];
-      const float* cls = buf + lane * K + 5;
+      const float* cls[NSB];  // a lane's row of sub-block sb; rows past the tile's end (never stored) fall back to row 0
 #pragma unroll
       for (int sb = 0; sb < NSB; ++sb) {
-        best[sb] = __float_as_uint(cls[sb * 32 * K] * conf[sb]);
+        cls[sb] = buf + (sb * 32 + lane < t.nrows ? sb * 32 + lane : 0) * K + 5;
+        best[sb] = __float_as_uint(cls[sb][0] * conf[sb]);
         bidx[sb] = 0;
       }
       for (int c = 1; c < K - 5; ++c) {
 #pragma unroll
-        for (int sb = 0; sb < NSB; ++sb) {  // rows past the tile's end read stale floats of the buffer; never stored
-          const unsigned pr = __float_as_uint(cls[sb * 32 * K + c] * conf[sb]);
+        for (int sb = 0; sb < NSB; ++sb) {
+          const unsigned pr = __float_as_uint(cls[sb][c] * conf[sb]);
           if (pr > best[sb]) {  // strict >: the first maximum wins
             best[sb] = pr;
             bidx[sb] = c;
