@@ -238,6 +238,7 @@ def run_cuda(args, cfg):
             cap_s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.graph(g_all, stream=cap_s):
                 for i in range(k):
+                    step._head(dl)              # label-only loss kernel on the side stream, beside the decode
                     if i in ev_d0:
                         ev_d0[i].record()
                     step._decode(dh)
@@ -277,6 +278,14 @@ def run_cuda(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = batch * world * k / (total_ms_max * 1e-3)
+    # per-rank view (N > 1): every rank's own decode time and timed-region length.  The step ends with a reduce that aligns the
+    # ranks, so the slowest GPU's decode sets everybody's step; these numbers say whether that or the reduce is the difference to N=1
+    per_rank = None
+    if distributed:
+        mine = torch.tensor([sum(decode_ms) / len(decode_ms), total_ms / k], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"decode_ms": [round(float(x[0]), 4) for x in allr], "ms_per_step": [round(float(x[1]), 4) for x in allr]}
 
     # ---- e2e: host buffers -> public API -> host results, copies inside the timed region --------------------
     out = step.out
@@ -445,6 +454,8 @@ def run_cuda(args, cfg):
                          "step_achieved": alg_bytes * world / (total_ms_max / k * 1e-3) / 1e9 / world,
                          "step_frac": alg_bytes / (total_ms_max / k * 1e-3) / 1e9 / peak},
         }
+        if per_rank is not None:
+            line["config"]["per_rank"] = per_rank
         if not args.no_cpu_baseline and world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             v, med, reps, backend = time_cpu_reference(cfg, args.cpu_sample, 0, args.cpu_budget, 3, 1)

@@ -377,10 +377,10 @@ extern "C" int64_t fvb_yolov3_saved_conf_floats(const fvb_yolo_geom* geom) {
   return (int64_t)g.B * g.row_off[g.L];
 }
 
-extern "C" int fvb_yolov3_loss_train_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
-                                         int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
-                                         const double* d_conf_bce0, double* d_partials, float* d_out_loss,
-                                         float* d_saved_conf, void* d_ws, void* stream) {
+static int run_yolov3_loss(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                           int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                           const double* d_conf_bce0, double* d_partials, float* d_out_loss,
+                           float* d_saved_conf, void* d_ws, void* stream, bool prepared) {
   FVB_REQUIRE(d_heads && d_partials && d_ws, "yolov3_loss: NULL pointer");
   FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "yolov3_loss: num_labels=%lld", (long long)num_labels);
   FVB_REQUIRE(num_labels == 0 || d_labels, "yolov3_loss: labels NULL");
@@ -447,16 +447,48 @@ extern "C" int fvb_yolov3_loss_train_f32(const fvb_yolo_geom* geom, const float*
       lp.conf_begin[l] = l < g.L ? fp.level_begin[l] : 0;
       lp.conf_end[l] = l < g.L ? fp.level_end[l] : 0;
     }
-    loss_prep_kernel<<<1, 1024, 0, s>>>(d_labels, lp.T, lp.flags);
+    if (!prepared) {
+      loss_prep_kernel<<<1, 1024, 0, s>>>(d_labels, lp.T, lp.flags);
+      count_launch();
+    }
     dim3 grid((unsigned)match_blocks, (unsigned)g.L);
     loss_match_kernel<<<grid, kLossThreads, 0, s>>>(lp);
-    count_launch(2);
+    count_launch();
   }
   fp.match_blocks = match_blocks;
   fp.match_ws = lp.match_ws;
   loss_finalize_kernel<<<1, 1024, 0, s>>>(fp);
   count_launch();
   return check_launch("yolov3_loss");
+}
+
+extern "C" int fvb_yolov3_loss_train_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                         int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                                         const double* d_conf_bce0, double* d_partials, float* d_out_loss,
+                                         float* d_saved_conf, void* d_ws, void* stream) {
+  return run_yolov3_loss(geom, d_heads, d_labels, num_labels, ratio_box, ratio_conf, ratio_cls, d_conf_bce0, d_partials,
+                         d_out_loss, d_saved_conf, d_ws, stream, false);
+}
+
+// The label-only part of the loss (is the label list grouped by image? -- what lets the duplicate-cell scans stop early),
+// split off so that a caller can enqueue it BEFORE the heads exist (e.g. next to the decode kernel) and keep it off the
+// loss branch's critical path; fvb_yolov3_loss_prepared_f32 then runs the rest on the same workspace.
+extern "C" int fvb_yolov3_loss_prep_f32(const float* d_labels, int64_t num_labels, void* d_ws, void* stream) {
+  FVB_REQUIRE(d_ws != nullptr && ((uintptr_t)d_ws & 255) == 0, "yolov3_loss_prep: workspace must be non-NULL and 256-byte aligned");
+  FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "yolov3_loss_prep: num_labels=%lld", (long long)num_labels);
+  FVB_REQUIRE(num_labels == 0 || d_labels, "yolov3_loss_prep: labels NULL");
+  if (num_labels == 0) return FVB_OK;
+  loss_prep_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_labels, (int)num_labels, (int*)d_ws);
+  count_launch();
+  return check_launch("yolov3_loss_prep");
+}
+
+extern "C" int fvb_yolov3_loss_prepared_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                            int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                                            const double* d_conf_bce0, double* d_partials, float* d_out_loss, void* d_ws,
+                                            void* stream) {
+  return run_yolov3_loss(geom, d_heads, d_labels, num_labels, ratio_box, ratio_conf, ratio_cls, d_conf_bce0, d_partials,
+                         d_out_loss, nullptr, d_ws, stream, true);
 }
 
 extern "C" int fvb_yolov3_loss_combine_f32(const fvb_yolo_geom* geom, int64_t batch_global, const double* d_partials,

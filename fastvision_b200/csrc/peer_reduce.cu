@@ -72,9 +72,13 @@ __global__ void __launch_bounds__(32) peer_reduce_combine_kernel(const PeerParam
   }
   e = __shfl_sync(0xffffffffu, e, 0);
   const int s = (int)(e & 1ull);
-  if (tid < p.n) mine->slot[s].vals[tid] = p.partials[tid];
-  __threadfence_system();
-  __syncwarp();
+  // one thread publishes: plain stores of the values, then ONE release store of the flag orders them system-wide (a
+  // separate __threadfence_system() by the whole warp in front of it cost a second system-scope barrier on the critical path)
+  const double mv = tid < p.n ? p.partials[tid] : 0.0;
+  for (int i = 0; i < p.n; ++i) {
+    const double v = __shfl_sync(0xffffffffu, mv, i);
+    if (tid == 0) mine->slot[s].vals[i] = v;
+  }
   if (tid == 0) st_release_sys(&mine->slot[s].flag, e);
   // wait for every peer's epoch-e publication (lane <-> peer)
   bool ok = true;

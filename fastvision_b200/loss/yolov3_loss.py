@@ -59,20 +59,31 @@ class Yolov3Loss(nn.Module):
             self._ctx = DecodeContext(y_pred, self.anchor_levels, self.backbone_stride_levels)
         return self._ctx
 
-    def forward(self, y_pred, y_true, conf_bce0=None, ctx=None, out=None, partials=None):
+    def prepare(self, y_true, ctx):
+        """The label-only part of ``forward`` (fvb_yolov3_loss_prep_f32), enqueued on the current stream: a caller that has the
+        labels before the heads (ValStep: beside the decode) runs it early and then calls ``forward(..., prepared=True)``
+        with the same labels and ``ctx`` on the same stream."""
+        labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
+        lib = _lib.load()
+        ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, labels.size(0)), ctx.device, "yolov3_loss")
+        with torch.cuda.device(ctx.device):
+            _lib.check(lib.fvb_yolov3_loss_prep_f32(_lib.dptr(labels), labels.size(0), _lib.dptr(ws), _lib.stream()), "yolov3_loss_prep")
+
+    def forward(self, y_pred, y_true, conf_bce0=None, ctx=None, out=None, partials=None, prepared=False):
         """y_pred: list of raw [B,A,H,W,K]; y_true [T,6] = [batch_idx, cls, xc, yc, w, h] -> Tensor[1].
 
         ``conf_bce0``: partials written by ``yolov3_decode(..., want_bce0=True)`` over the same heads; when
-        given the loss does not touch the dense objectness channel again.
+        given the loss does not touch the dense objectness channel again.  ``prepared``: ``prepare`` already ran for
+        these labels (inference form only).
         """
         heads = [_lib.require_cuda(h, "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
         labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
         ctx = ctx or self._context(heads)
         if torch.is_grad_enabled() and any(h.requires_grad for h in heads):
             return _Yolov3LossFn.apply(self, labels.detach(), ctx, conf_bce0, out, partials, None, *heads)
-        return self._forward_impl(heads, labels, ctx, conf_bce0, out, partials)
+        return self._forward_impl(heads, labels, ctx, conf_bce0, out, partials, prepared=prepared)
 
-    def _forward_impl(self, heads, labels, ctx, conf_bce0, out, partials, saved_conf=None):
+    def _forward_impl(self, heads, labels, ctx, conf_bce0, out, partials, saved_conf=None, prepared=False):
         dev = ctx.device
         t = labels.size(0)
         if out is None:
@@ -82,10 +93,16 @@ class Yolov3Loss(nn.Module):
         lib = _lib.load()
         ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, t), dev, "yolov3_loss")
         with torch.cuda.device(dev):
-            _lib.check(lib.fvb_yolov3_loss_train_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
-                                                     float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
-                                                     _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
-                                                     _lib.dptr(saved_conf), _lib.dptr(ws), _lib.stream()), "yolov3_loss")
+            if prepared and saved_conf is None:
+                _lib.check(lib.fvb_yolov3_loss_prepared_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
+                                                            float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
+                                                            _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
+                                                            _lib.dptr(ws), _lib.stream()), "yolov3_loss")
+            else:
+                _lib.check(lib.fvb_yolov3_loss_train_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
+                                                         float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
+                                                         _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
+                                                         _lib.dptr(saved_conf), _lib.dptr(ws), _lib.stream()), "yolov3_loss")
         self.partials = partials
         return out
 

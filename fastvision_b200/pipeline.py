@@ -70,6 +70,23 @@ class ValStep:
         self._side = torch.cuda.Stream(device=dev)
         self._ev_decoded = torch.cuda.Event()
         self._ev_loss = torch.cuda.Event()
+        self._ev_start = torch.cuda.Event()
+        self._prepared = False
+
+    def _head(self, labels):
+        """Optional first part of a step, before ``_decode``: the label-only kernel of the loss goes onto the side stream
+        now, beside the decode, instead of opening the loss branch afterwards (that branch, with the data-parallel reduce at
+        its end, is the step's critical tail on more than one GPU)."""
+        if not self._distributed():
+            # on one GPU the NMS branch is the tail, and a loss branch that opens 7 us earlier only makes loss_match's CTAs
+            # compete with the NMS CTAs for SM slots right after the decode (measured: step 0.362 -> 0.370 ms)
+            return
+        main = torch.cuda.current_stream()
+        self._ev_start.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_start)
+            self.loss_fn.prepare(labels, self.ctx)
+        self._prepared = True
 
     def _distributed(self):
         return self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -89,7 +106,8 @@ class ValStep:
         self._ev_decoded.record(main)
         with torch.cuda.stream(self._side):
             self._side.wait_event(self._ev_decoded)
-            self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
+            self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"], prepared=self._prepared)
+            self._prepared = False
             if reduce_inside:
                 self._reduce()
             self._ev_loss.record(self._side)
@@ -120,6 +138,7 @@ class ValStep:
         return self._peer_reducer
 
     def _run(self, heads, labels):
+        self._head(labels)
         self._decode(heads)
         self._tail(heads, labels, reduce_inside=True)
         return self.out
@@ -162,6 +181,7 @@ class ValStep:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             if not split_decode:
+                self._head(labels)
                 self._decode(heads)
             self._tail(heads, labels, reduce_inside=dist_graph)
         self.graph = g
