@@ -89,3 +89,57 @@ def test_demo_losses(ns):
     with contextlib.redirect_stdout(io.StringIO()):
         want_u = ns.load_demo("yolov3_u", "lossv3").ComputeLoss()(heads, labels, model)
     assert torch.equal(oracle.demo_loss.compute_loss(heads, labels, anchors, "u"), want_u)
+
+
+@pytest.mark.parametrize("seed", [5, 6, 7])
+def test_map_live_with_quirks(ns, seed):
+    """CalculateMAP.process_one / fetch of the real reference vs the oracle on fresh images, including the two quirks the
+    golden file does not hold: a class with targets but no detections (AP 0.5 at every threshold) and a single perfect
+    detection (0.995), metrics/map.py:85-141."""
+    g = torch.Generator().manual_seed(seed)
+    thr = np.linspace(0.5, 0.95, 10)
+    ref, ora = ns.metrics.CalculateMAP(thr), oracle.map_.MapOracle(thr)
+    for i in range(10):
+        nt = int(torch.randint(1, 6, (1,), generator=g))
+        tb = boxes(nt, g)
+        tc = torch.randint(0, 3, (nt, 1), generator=g).float()
+        y_true = torch.cat([tc, tb], 1)
+        preds = [torch.cat([tc[j] if float(torch.rand(1, generator=g)) < 0.8 else (tc[j] + 1) % 3, torch.rand(1, generator=g),
+                            tb[j] + torch.randn(4, generator=g) * 3]) for j in range(nt) for _ in range(int(torch.randint(0, 3, (1,), generator=g)))]
+        y_pred = torch.stack(preds).view(-1, 6) if preds else torch.zeros(0, 6)
+        n_ref, n_ora = len(ref.correct_all_images), len(ora.correct_all_images)
+        ref.process_one(y_pred, y_true)
+        ora.process_one(y_pred, y_true)
+        assert len(ref.correct_all_images) - n_ref == len(ora.correct_all_images) - n_ora
+        if len(ora.correct_all_images) > n_ora:
+            assert np.array_equal(ref.correct_all_images[-1], ora.correct_all_images[-1])
+    # class 7: targets only; class 8: one target, one perfect detection
+    quirk_true = torch.tensor([[7.0, 10, 10, 50, 50], [8.0, 60, 60, 90, 90]])
+    quirk_pred = torch.tensor([[8.0, 0.9, 60, 60, 90, 90]])
+    ref.process_one(quirk_pred, quirk_true)
+    ora.process_one(quirk_pred, quirk_true)
+    r_iou, r_cls, r_ids = ref.fetch()
+    o_iou, o_cls, o_ids = ora.fetch()
+    assert list(r_ids) == list(o_ids)
+    np.testing.assert_allclose(o_iou, r_iou, rtol=1e-12)
+    np.testing.assert_allclose(o_cls, r_cls, rtol=1e-12)
+    np.testing.assert_allclose(r_cls[list(r_ids).index(7)], 0.5, rtol=1e-12)
+    np.testing.assert_allclose(r_cls[list(r_ids).index(8)], 0.995, rtol=1e-12)
+
+
+@pytest.mark.parametrize("seed,shape", [(21, (2, 7, 6, 300, 50, 0.7)), (22, (1, 10, 9, 2000, 2000, 0.5))])
+def test_rpn_filter_proposals_live(ns, seed, shape):
+    """RPN.filter_proposals of the real reference (demos/faster_rcnn/models/rpn.py:168-208) vs the oracle on fresh inputs."""
+    import math
+    b, fh, fw, pre, post, thr = shape
+    base = torch.tensor(np.array([(math.sqrt(s ** 2 / r), s ** 2 / math.sqrt(s ** 2 / r)) for r in [1, 0.5, 2] for s in [128, 256, 512]],
+                                 dtype=np.float32))
+    rpn = ns.load_rpn().RPN(training=False, base_anchors=base, backbone_stride=16, in_channels=8, rpn_pre_nms_top_n=pre,
+                            rpn_post_nms_top_n=post, rpn_nms_thresh=thr)
+    g = torch.Generator().manual_seed(seed)
+    cls, reg = synth.make_rpn_inputs(b, fh, fw, 9, g)
+    want = rpn.filter_proposals(cls, reg, rpn.make_anchors_xywh(fh, fw, "cpu"), fh, fw)
+    got = oracle.rpn.filter_proposals(cls, reg, base / 16, pre, post, thr)
+    assert len(got) == len(want)
+    for a, w in zip(got, want):
+        assert torch.equal(a, w)
