@@ -143,3 +143,27 @@ def test_rpn_filter_proposals_live(ns, seed, shape):
     assert len(got) == len(want)
     for a, w in zip(got, want):
         assert torch.equal(a, w)
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_demo_and_frcnn_nms_live(ns, seed):
+    """The demos' class-aware NMS front-ends (demos/yolov3_u/utils/nms.py:5-98) and the Faster R-CNN final NMS
+    (demos/faster_rcnn/utils/nms.py:5-39) of the real reference vs the oracle on fresh inputs."""
+    g = torch.Generator().manual_seed(seed)
+    labels = synth.make_labels(SMALL, 3, g)
+    heads = synth.make_heads(SMALL, 3, labels, g)
+    res = ns.decode(heads, SMALL.anchors_levels(), SMALL.strides, SMALL.num_classes)
+    demo = ns.load_demo("yolov3_u", "nms")
+    for i in range(3):
+        p = res[i].clone()
+        p[:, :4] = ns.tools.xywh2xyxy(p[:, :4])
+        assert torch.equal(oracle.nms.nms_demo(p.clone(), 0.1, 0.3, 50), demo.non_max_suppression(p.clone(), 0.1, 0.3, 50))
+    want = demo.non_max_suppression_batch([res[i].clone() for i in range(3)], 0.1, 0.3, 50)
+    got = oracle.nms.nms_demo_batch([res[i].clone() for i in range(3)], 0.1, 0.3, 50)
+    assert len(want) == len(got) and all(torch.equal(a, b) for a, b in zip(got, want))
+    frcnn = ns.load_demo("faster_rcnn", "nms")
+    n = 200
+    ctr = (torch.rand(n // 4, 2, generator=g) * 300 + 50).repeat_interleave(4, 0) + torch.randn(n, 2, generator=g) * 6
+    wh = torch.rand(n, 2, generator=g) * 60 + 20
+    pred = torch.cat([ctr - wh / 2, ctr + wh / 2, torch.randint(0, 4, (n, 1), generator=g).float(), torch.rand(n, 1, generator=g)], 1)
+    assert torch.equal(oracle.nms.nms_frcnn(pred.clone(), 0.25, 0.45, 100), frcnn.non_max_suppression(pred.clone(), 0.25, 0.45, 100))
