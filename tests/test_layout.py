@@ -84,3 +84,22 @@ def test_geometry_helpers_without_gpu():
     bad = _lib.make_geom(8, 3, cfg.feat, cfg.feat, cfg.strides, cfg.anchors_levels())
     assert lib.fvb_yolo_rows_per_image(bad) == -1
     assert b"channels" in lib.fvb_last_error()
+
+
+def test_header_is_plain_c_and_links_from_gcc(tmp_path):
+    """include/fvb200.h compiles as C (not only C++) and a gcc-built program links against libfvb200.so and calls it."""
+    import shutil
+    import subprocess
+    from fastvision_b200 import _build, _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not installed")
+    _build.build()
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cuda_inc = "/usr/local/cuda/include"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+           os.path.join(ROOT, "tests", "abi_smoke.c"), "-o", exe, "-L", libdir, "-l:libfvb200.so", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
