@@ -59,9 +59,8 @@ _SIGS = {
     "fvb_yolov3_loss_workspace_bytes": (C.c_size_t, [C.POINTER(Geom), C.c_int64]),
     "fvb_yolov3_loss_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_float, C.c_float, C.c_float,
                                       _P, _P, _P, _P, _P]),
-    "fvb_yolov3_loss_prep_f32": (C.c_int, [_P, C.c_int64, _P, _P]),
-    "fvb_yolov3_loss_prepared_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_float, C.c_float, C.c_float,
-                                               _P, _P, _P, _P, _P]),
+    "fvb_yolov3_loss_match_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, _P, _P]),
+    "fvb_yolov3_loss_finish_f32": (C.c_int, [C.POINTER(Geom), C.c_int64, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     "fvb_yolov3_saved_conf_floats": (C.c_int64, [C.POINTER(Geom)]),
     "fvb_yolov3_loss_train_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_float, C.c_float, C.c_float,
                                             _P, _P, _P, _P, _P, _P]),

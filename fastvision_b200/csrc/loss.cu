@@ -39,7 +39,10 @@ __global__ void loss_prep_kernel(const float* labels, int T, int* flags) {
   for (int t = threadIdx.x; t + 1 < T; t += blockDim.x)
     if ((int)labels[(size_t)t * 6] > (int)labels[(size_t)(t + 1) * 6]) bad = 1;
   __syncthreads();
-  if (threadIdx.x == 0) flags[0] = bad ? 0 : 1;
+  if (threadIdx.x == 0) {
+    flags[0] = bad ? 0 : 1;
+    flags[1] = 0;  // arrival counter of loss_finish_kernel
+  }
 }
 
 __global__ void __launch_bounds__(kLossThreads) loss_match_kernel(const LossParams p) {
@@ -258,6 +261,67 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const FinalizeParam
     p.out_loss[0] = combine_loss(p.g, p.partials, p.batch_global, p.r_box, p.r_conf, p.r_cls);
 }
 
+// The second half of the two-part loss (fvb_yolov3_loss_match_f32 / fvb_yolov3_loss_finish_f32): loss_match ran EARLY (it reads
+// only raw heads and labels) without folding the decode's objectness partials, so this kernel does that sum -- grid (kFinishCtas,
+// L): CTA (x, l) sums slice x of level l's partials in a fixed order -- and the last CTA to arrive reduces the slices and
+// loss_match's per-CTA columns (again in index order: the result does not depend on which CTA is last) and forms the scalar.
+constexpr int kFinishCtas = 48;
+struct FinishParams {
+  FinalizeParams f;
+  double* slices;  // [L][kFinishCtas]
+  int* counter;    // zero on entry (loss_prep), left zero
+};
+
+__global__ void __launch_bounds__(256) loss_finish_kernel(const FinishParams p) {
+  __shared__ double scratch[32];
+  __shared__ int last;
+  const int l = blockIdx.y, x = blockIdx.x;
+  {
+    const int n = p.f.level_end[l] - p.f.level_begin[l];
+    const int per = (n + kFinishCtas - 1) / kFinishCtas;
+    const int beg = p.f.level_begin[l] + x * per;
+    const int cnt = max(0, min(per, p.f.level_end[l] - beg));
+    double cs = strided_sum(p.f.conf0 + beg, cnt);
+    cs = block_sum(cs, scratch);
+    if (threadIdx.x == 0) p.slices[l * kFinishCtas + x] = cs;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(p.counter, 1) == (int)(gridDim.x * gridDim.y) - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int TA = p.f.match_blocks;
+  for (int wc = warp; wc < p.f.g.L * 4; wc += 8) {  // one warp per (level, component)
+    const int ll = wc >> 2, c = wc & 3;
+    double s0 = 0.0, s1 = 0.0;
+    if (TA > 0) {
+      const double* ws = p.f.match_ws + (size_t)ll * TA * 4 + c;
+      int i = lane;
+      for (; i + 32 < TA; i += 64) {
+        s0 += ws[(size_t)i * 4];
+        s1 += ws[(size_t)(i + 32) * 4];
+      }
+      if (i < TA) s0 += ws[(size_t)i * 4];
+    }
+    double tot = warp_sum(s0 + s1);
+    if (c == 2) {
+      double d = 0.0;
+      for (int i = lane; i < kFinishCtas; i += 32) d += __ldcg(&p.slices[ll * kFinishCtas + i]);  // written by other CTAs: L2
+      tot += warp_sum(d);
+    }
+    if (lane == 0) p.f.partials[wc] = tot;
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (p.f.out_loss != nullptr)
+      p.f.out_loss[0] = combine_loss(p.f.g, p.f.partials, p.f.batch_global, p.f.r_box, p.f.r_conf, p.f.r_cls);
+    p.counter[0] = 0;
+  }
+}
+
 struct CombineParams {
   Geom g;
   const double* partials;
@@ -360,6 +424,7 @@ extern "C" size_t fvb_yolov3_loss_workspace_bytes(const fvb_yolo_geom* geom, int
   size_t parts = 0;
   for (int l = 0; l < g.L; ++l) parts += (size_t)stream_chunks(g, l) * g.B;
   o = align_up(o + parts * 8, 256);
+  o = align_up(o + (size_t)g.L * kFinishCtas * 8, 256);  // slice sums of the two-part form
   return o + 256;
 }
 
@@ -377,18 +442,24 @@ extern "C" int64_t fvb_yolov3_saved_conf_floats(const fvb_yolo_geom* geom) {
   return (int64_t)g.B * g.row_off[g.L];
 }
 
+enum { kLossAll = 0, kLossMatchOnly = 1, kLossFinishOnly = 2 };
+
 static int run_yolov3_loss(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
                            int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
                            const double* d_conf_bce0, double* d_partials, float* d_out_loss,
-                           float* d_saved_conf, void* d_ws, void* stream, bool prepared) {
-  FVB_REQUIRE(d_heads && d_partials && d_ws, "yolov3_loss: NULL pointer");
+                           float* d_saved_conf, void* d_ws, void* stream, int mode) {
+  FVB_REQUIRE(d_ws != nullptr, "yolov3_loss: NULL workspace");
+  FVB_REQUIRE(mode == kLossMatchOnly || d_partials != nullptr, "yolov3_loss: NULL partials");
+  FVB_REQUIRE(mode == kLossFinishOnly || d_heads != nullptr, "yolov3_loss: NULL heads");
+  FVB_REQUIRE(mode != kLossFinishOnly || d_conf_bce0 != nullptr, "yolov3_loss_finish: needs the decode's objectness partials");
   FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "yolov3_loss: num_labels=%lld", (long long)num_labels);
-  FVB_REQUIRE(num_labels == 0 || d_labels, "yolov3_loss: labels NULL");
+  FVB_REQUIRE(num_labels == 0 || d_labels || mode == kLossFinishOnly, "yolov3_loss: labels NULL");
   FVB_REQUIRE(((uintptr_t)d_ws & 255) == 0, "yolov3_loss: workspace must be 256-byte aligned");
   LossParams lp;
-  int rc = make_geom(geom, d_heads, &lp.g);
+  int rc = make_geom(geom, mode == kLossFinishOnly ? nullptr : d_heads, &lp.g);
   if (rc != FVB_OK) return rc;
-  for (int l = 0; l < lp.g.L; ++l) FVB_REQUIRE(d_heads[l] != nullptr, "yolov3_loss: head %d is NULL", l);
+  if (mode != kLossFinishOnly)
+    for (int l = 0; l < lp.g.L; ++l) FVB_REQUIRE(d_heads[l] != nullptr, "yolov3_loss: head %d is NULL", l);
   FVB_REQUIRE(lp.g.B >= 1, "yolov3_loss: empty batch");
   FVB_REQUIRE(!lp.g.nchw, "yolov3_loss: heads must be [B,A,H,W,K] (FVB_HEAD_BAHWK)");
   const Geom& g = lp.g;
@@ -399,6 +470,10 @@ static int run_yolov3_loss(const fvb_yolo_geom* geom, const float* const* d_head
   lp.match_ws = (double*)(w + o);
   o = align_up(o + (size_t)g.L * (size_t)num_labels * g.A * 4 * 8, 256);
   double* stream_parts = (double*)(w + o);
+  size_t parts = 0;
+  for (int l = 0; l < g.L; ++l) parts += (size_t)stream_chunks(g, l) * g.B;
+  o = align_up(o + parts * 8, 256);
+  double* finish_slices = (double*)(w + o);
   lp.labels = d_labels;
   lp.T = (int)num_labels;
 
@@ -410,7 +485,10 @@ static int run_yolov3_loss(const fvb_yolo_geom* geom, const float* const* d_head
   fp.r_conf = ratio_conf;
   fp.r_cls = ratio_cls;
   fp.batch_global = g.B;
-  if (d_conf_bce0 && d_saved_conf == nullptr) {
+  if (mode == kLossMatchOnly) {
+    fp.conf0 = nullptr;  // loss_match folds nothing: the objectness partials do not exist yet
+    for (int l = 0; l < FVB_MAX_LEVELS; ++l) fp.level_begin[l] = fp.level_end[l] = 0;
+  } else if (d_conf_bce0 && d_saved_conf == nullptr) {
     fp.conf0 = d_conf_bce0;
     const int tr = decode_tile_rows(g.K);  // the decode kernel wrote one partial per tile, level-major
     int t = 0;
@@ -441,22 +519,32 @@ static int run_yolov3_loss(const fvb_yolo_geom* geom, const float* const* d_head
 
   const int wpb = kLossThreads / 32;
   const int match_blocks = (int)(((long long)lp.T * g.A + wpb - 1) / wpb);
+  fp.match_blocks = match_blocks;
+  fp.match_ws = lp.match_ws;
+  if (mode == kLossFinishOnly) {
+    FinishParams q;
+    q.f = fp;
+    q.slices = finish_slices;
+    q.counter = lp.flags + 1;
+    loss_finish_kernel<<<dim3(kFinishCtas, (unsigned)g.L), 256, 0, s>>>(q);
+    count_launch();
+    return check_launch("yolov3_loss_finish");
+  }
+  if (lp.T > 0 || mode == kLossMatchOnly) {
+    loss_prep_kernel<<<1, 1024, 0, s>>>(d_labels, lp.T, lp.flags);  // (also zeroes the finish kernel's arrival counter)
+    count_launch();
+  }
   if (lp.T > 0) {
     lp.conf0 = fp.conf0;
     for (int l = 0; l < FVB_MAX_LEVELS; ++l) {
       lp.conf_begin[l] = l < g.L ? fp.level_begin[l] : 0;
       lp.conf_end[l] = l < g.L ? fp.level_end[l] : 0;
     }
-    if (!prepared) {
-      loss_prep_kernel<<<1, 1024, 0, s>>>(d_labels, lp.T, lp.flags);
-      count_launch();
-    }
     dim3 grid((unsigned)match_blocks, (unsigned)g.L);
     loss_match_kernel<<<grid, kLossThreads, 0, s>>>(lp);
     count_launch();
   }
-  fp.match_blocks = match_blocks;
-  fp.match_ws = lp.match_ws;
+  if (mode == kLossMatchOnly) return check_launch("yolov3_loss_match");
   loss_finalize_kernel<<<1, 1024, 0, s>>>(fp);
   count_launch();
   return check_launch("yolov3_loss");
@@ -467,28 +555,25 @@ extern "C" int fvb_yolov3_loss_train_f32(const fvb_yolo_geom* geom, const float*
                                          const double* d_conf_bce0, double* d_partials, float* d_out_loss,
                                          float* d_saved_conf, void* d_ws, void* stream) {
   return run_yolov3_loss(geom, d_heads, d_labels, num_labels, ratio_box, ratio_conf, ratio_cls, d_conf_bce0, d_partials,
-                         d_out_loss, d_saved_conf, d_ws, stream, false);
+                         d_out_loss, d_saved_conf, d_ws, stream, kLossAll);
 }
 
-// The label-only part of the loss (is the label list grouped by image? -- what lets the duplicate-cell scans stop early),
-// split off so that a caller can enqueue it BEFORE the heads exist (e.g. next to the decode kernel) and keep it off the
-// loss branch's critical path; fvb_yolov3_loss_prepared_f32 then runs the rest on the same workspace.
-extern "C" int fvb_yolov3_loss_prep_f32(const float* d_labels, int64_t num_labels, void* d_ws, void* stream) {
-  FVB_REQUIRE(d_ws != nullptr && ((uintptr_t)d_ws & 255) == 0, "yolov3_loss_prep: workspace must be non-NULL and 256-byte aligned");
-  FVB_REQUIRE(num_labels >= 0 && num_labels < (1ll << 24), "yolov3_loss_prep: num_labels=%lld", (long long)num_labels);
-  FVB_REQUIRE(num_labels == 0 || d_labels, "yolov3_loss_prep: labels NULL");
-  if (num_labels == 0) return FVB_OK;
-  loss_prep_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_labels, (int)num_labels, (int*)d_ws);
-  count_launch();
-  return check_launch("yolov3_loss_prep");
+// The same loss in two parts.  Target assignment and the matched-row terms read only the RAW heads and the labels, so
+// fvb_yolov3_loss_match_f32 can be enqueued beside the decode kernel and hide under it; what needs the decode is only the sum of
+// its objectness partials: fvb_yolov3_loss_finish_f32 (same d_ws, same num_labels, after both) does that sum, reduces the
+// matched terms and writes {S_cls, S_box, S_conf, M} per level and the scalar.  match + finish == fvb_yolov3_loss_f32 up to
+// the association of the fp64 sums (both orders are fixed, so each form is bit-reproducible).
+extern "C" int fvb_yolov3_loss_match_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                         int64_t num_labels, void* d_ws, void* stream) {
+  return run_yolov3_loss(geom, d_heads, d_labels, num_labels, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, d_ws, stream,
+                         kLossMatchOnly);
 }
 
-extern "C" int fvb_yolov3_loss_prepared_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
-                                            int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
-                                            const double* d_conf_bce0, double* d_partials, float* d_out_loss, void* d_ws,
-                                            void* stream) {
-  return run_yolov3_loss(geom, d_heads, d_labels, num_labels, ratio_box, ratio_conf, ratio_cls, d_conf_bce0, d_partials,
-                         d_out_loss, nullptr, d_ws, stream, true);
+extern "C" int fvb_yolov3_loss_finish_f32(const fvb_yolo_geom* geom, int64_t num_labels, float ratio_box, float ratio_conf,
+                                          float ratio_cls, const double* d_conf_bce0, double* d_partials, float* d_out_loss,
+                                          void* d_ws, void* stream) {
+  return run_yolov3_loss(geom, nullptr, nullptr, num_labels, ratio_box, ratio_conf, ratio_cls, d_conf_bce0, d_partials,
+                         d_out_loss, nullptr, d_ws, stream, kLossFinishOnly);
 }
 
 extern "C" int fvb_yolov3_loss_combine_f32(const fvb_yolo_geom* geom, int64_t batch_global, const double* d_partials,

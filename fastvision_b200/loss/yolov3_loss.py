@@ -59,31 +59,48 @@ class Yolov3Loss(nn.Module):
             self._ctx = DecodeContext(y_pred, self.anchor_levels, self.backbone_stride_levels)
         return self._ctx
 
-    def prepare(self, y_true, ctx):
-        """The label-only part of ``forward`` (fvb_yolov3_loss_prep_f32), enqueued on the current stream: a caller that has the
-        labels before the heads (ValStep: beside the decode) runs it early and then calls ``forward(..., prepared=True)``
-        with the same labels and ``ctx`` on the same stream."""
+    def match(self, y_pred, y_true, ctx):
+        """First part of the two-part inference form (fvb_yolov3_loss_match_f32): target assignment and matched-row terms from
+        the RAW heads and the labels, enqueued on the current stream -- a caller that also decodes these heads (ValStep) runs
+        it beside the decode.  ``finish`` completes the loss once the decode's objectness partials exist."""
+        heads = [_lib.require_cuda(h.detach(), "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
         labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
         lib = _lib.load()
         ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, labels.size(0)), ctx.device, "yolov3_loss")
         with torch.cuda.device(ctx.device):
-            _lib.check(lib.fvb_yolov3_loss_prep_f32(_lib.dptr(labels), labels.size(0), _lib.dptr(ws), _lib.stream()), "yolov3_loss_prep")
+            _lib.check(lib.fvb_yolov3_loss_match_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), labels.size(0),
+                                                     _lib.dptr(ws), _lib.stream()), "yolov3_loss_match")
 
-    def forward(self, y_pred, y_true, conf_bce0=None, ctx=None, out=None, partials=None, prepared=False):
+    def finish(self, num_labels, ctx, conf_bce0, out=None, partials=None):
+        """Second part (fvb_yolov3_loss_finish_f32), after ``match`` and the decode on the same stream order."""
+        dev = ctx.device
+        if out is None:
+            out = torch.empty(1, dtype=torch.float32, device=dev)
+        if partials is None:
+            partials = torch.empty(ctx.geom.levels, 4, dtype=torch.float64, device=dev)
+        lib = _lib.load()
+        ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, int(num_labels)), dev, "yolov3_loss")
+        with torch.cuda.device(dev):
+            _lib.check(lib.fvb_yolov3_loss_finish_f32(ctx.geom, int(num_labels), float(self.ratio_box), float(self.ratio_conf),
+                                                      float(self.ratio_cls), _lib.dptr(conf_bce0), _lib.dptr(partials),
+                                                      _lib.dptr(out), _lib.dptr(ws), _lib.stream()), "yolov3_loss_finish")
+        self.partials = partials
+        return out
+
+    def forward(self, y_pred, y_true, conf_bce0=None, ctx=None, out=None, partials=None):
         """y_pred: list of raw [B,A,H,W,K]; y_true [T,6] = [batch_idx, cls, xc, yc, w, h] -> Tensor[1].
 
         ``conf_bce0``: partials written by ``yolov3_decode(..., want_bce0=True)`` over the same heads; when
-        given the loss does not touch the dense objectness channel again.  ``prepared``: ``prepare`` already ran for
-        these labels (inference form only).
+        given the loss does not touch the dense objectness channel again.
         """
         heads = [_lib.require_cuda(h, "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
         labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
         ctx = ctx or self._context(heads)
         if torch.is_grad_enabled() and any(h.requires_grad for h in heads):
             return _Yolov3LossFn.apply(self, labels.detach(), ctx, conf_bce0, out, partials, None, *heads)
-        return self._forward_impl(heads, labels, ctx, conf_bce0, out, partials, prepared=prepared)
+        return self._forward_impl(heads, labels, ctx, conf_bce0, out, partials)
 
-    def _forward_impl(self, heads, labels, ctx, conf_bce0, out, partials, saved_conf=None, prepared=False):
+    def _forward_impl(self, heads, labels, ctx, conf_bce0, out, partials, saved_conf=None):
         dev = ctx.device
         t = labels.size(0)
         if out is None:
@@ -93,16 +110,10 @@ class Yolov3Loss(nn.Module):
         lib = _lib.load()
         ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, t), dev, "yolov3_loss")
         with torch.cuda.device(dev):
-            if prepared and saved_conf is None:
-                _lib.check(lib.fvb_yolov3_loss_prepared_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
-                                                            float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
-                                                            _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
-                                                            _lib.dptr(ws), _lib.stream()), "yolov3_loss")
-            else:
-                _lib.check(lib.fvb_yolov3_loss_train_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
-                                                         float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
-                                                         _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
-                                                         _lib.dptr(saved_conf), _lib.dptr(ws), _lib.stream()), "yolov3_loss")
+            _lib.check(lib.fvb_yolov3_loss_train_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
+                                                     float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
+                                                     _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
+                                                     _lib.dptr(saved_conf), _lib.dptr(ws), _lib.stream()), "yolov3_loss")
         self.partials = partials
         return out
 

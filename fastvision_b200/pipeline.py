@@ -71,22 +71,6 @@ class ValStep:
         self._ev_decoded = torch.cuda.Event()
         self._ev_loss = torch.cuda.Event()
         self._ev_start = torch.cuda.Event()
-        self._prepared = False
-
-    def _head(self, labels):
-        """Optional first part of a step, before ``_decode``: the label-only kernel of the loss goes onto the side stream
-        now, beside the decode, instead of opening the loss branch afterwards (that branch, with the data-parallel reduce at
-        its end, is the step's critical tail on more than one GPU)."""
-        if not self._distributed():
-            # on one GPU the NMS branch is the tail, and a loss branch that opens 7 us earlier only makes loss_match's CTAs
-            # compete with the NMS CTAs for SM slots right after the decode (measured: step 0.362 -> 0.370 ms)
-            return
-        main = torch.cuda.current_stream()
-        self._ev_start.record(main)
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(self._ev_start)
-            self.loss_fn.prepare(labels, self.ctx)
-        self._prepared = True
 
     def _distributed(self):
         return self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -94,20 +78,29 @@ class ValStep:
 
     def _decode(self, heads):
         ctx, o = self.ctx, self.out
+        self._ev_start.record(torch.cuda.current_stream())     # what the early half of the loss waits for (see _tail)
         yolov3_decode(heads, self.anchors_per_level, self.strides, precise=self.precise, ctx=ctx, out=o["results"],
                       conf_thres=self.conf_thres, want_bce0=True)
 
-    def _tail(self, heads, labels, reduce_inside=False):
-        """Everything after the decode: the NMS branch and the loss branch (second stream), joined at the end.
-        ``reduce_inside`` puts the data-parallel all-reduce + combine into the loss branch so that it hides under
-        the (longer) NMS branch; only possible when the tail is launched eagerly, not captured."""
+    def _tail(self, heads, labels, reduce_inside=False, early_match=False):
+        """Everything after the decode launch: the NMS branch and the loss branch (second stream), joined at the end.
+        ``reduce_inside`` puts the data-parallel all-reduce + combine into the loss branch.
+        ``early_match`` (only right after ``_decode`` in the same eager / captured sequence): the loss runs in its two-part
+        form -- target assignment and matched-row terms wait only for the step's START, so they run beside the decode kernel
+        (launched first) and hide under it; after the decode only the small objectness-partials sum + reduce remain, so the
+        loss branch is neither the step's tail on several GPUs nor a competitor of the NMS CTAs on one."""
         ctx, o = self.ctx, self.out
         main = torch.cuda.current_stream()
         self._ev_decoded.record(main)
         with torch.cuda.stream(self._side):
-            self._side.wait_event(self._ev_decoded)
-            self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"], prepared=self._prepared)
-            self._prepared = False
+            if early_match:
+                self._side.wait_event(self._ev_start)
+                self.loss_fn.match(heads, labels, ctx)
+                self._side.wait_event(self._ev_decoded)
+                self.loss_fn.finish(labels.size(0), ctx, ctx.bce0(), out=o["loss"], partials=o["partials"])
+            else:
+                self._side.wait_event(self._ev_decoded)
+                self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
             if reduce_inside:
                 self._reduce()
             self._ev_loss.record(self._side)
@@ -138,9 +131,8 @@ class ValStep:
         return self._peer_reducer
 
     def _run(self, heads, labels):
-        self._head(labels)
         self._decode(heads)
-        self._tail(heads, labels, reduce_inside=True)
+        self._tail(heads, labels, reduce_inside=True, early_match=True)
         return self.out
 
     def __call__(self, head_out: List[torch.Tensor], labels: torch.Tensor):
@@ -181,9 +173,8 @@ class ValStep:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             if not split_decode:
-                self._head(labels)
                 self._decode(heads)
-            self._tail(heads, labels, reduce_inside=dist_graph)
+            self._tail(heads, labels, reduce_inside=dist_graph, early_match=not split_decode)
         self.graph = g
 
         if split_decode:

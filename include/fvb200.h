@@ -203,15 +203,16 @@ int fvb_yolov3_loss_f32(const fvb_yolo_geom* geom, const float* const* d_heads, 
                         int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
                         const double* d_conf_bce0, double* d_partials, float* d_out_loss, void* d_ws,
                         void* stream);
-/* The same call in two parts: fvb_yolov3_loss_prep_f32 is the label-only part (are the labels grouped by image, the order
- * datasets/detection_dataloader.py:88-103's collate_fn produces? -- lets the duplicate-cell scans of yolov3_loss.py:61 stop
- * early) and may be enqueued before the heads exist, e.g. beside the decode; fvb_yolov3_loss_prepared_f32 runs the rest
- * with the SAME d_ws and labels.  prep + prepared == fvb_yolov3_loss_f32, bit for bit. */
-int fvb_yolov3_loss_prep_f32(const float* d_labels, int64_t num_labels, void* d_ws, void* stream);
-int fvb_yolov3_loss_prepared_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
-                                 int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
-                                 const double* d_conf_bce0, double* d_partials, float* d_out_loss, void* d_ws,
-                                 void* stream);
+/* The same loss in two parts.  Target assignment and the matched-row terms (loss/yolov3_loss.py:44-61, :75-124) read only the raw
+ * heads and the labels: fvb_yolov3_loss_match_f32 may be enqueued beside fvb_yolo_decode_f32 and hides under it.  What needs the
+ * decode is only the sum of its objectness partials (:63-64): fvb_yolov3_loss_finish_f32 -- same d_ws and num_labels, ordered
+ * after both -- does that sum, reduces the matched terms and writes d_partials / d_out_loss as fvb_yolov3_loss_f32 would
+ * (equal up to the association of the fp64 sums; each form is bit-reproducible). */
+int fvb_yolov3_loss_match_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                              int64_t num_labels, void* d_ws, void* stream);
+int fvb_yolov3_loss_finish_f32(const fvb_yolo_geom* geom, int64_t num_labels, float ratio_box, float ratio_conf,
+                               float ratio_cls, const double* d_conf_bce0, double* d_partials, float* d_out_loss,
+                               void* d_ws, void* stream);
 /* Training form of the same call: additionally writes d_saved_conf ([fvb_yolov3_saved_conf_floats(geom)] f32, may be
  * NULL), a compact level-major copy [l][b][row] of the objectness logits, which fvb_yolov3_loss_backward_f32 then reads
  * instead of striding through the heads again.  With d_saved_conf the call always streams channel 4 itself. */

@@ -396,6 +396,25 @@ def test_val_step_config1_matches_oracle_and_graph_replay():
         assert torch.equal(out["boxes"][i, :kk], snap["boxes"][i, :kk])
 
 
+@pytest.mark.parametrize("cfg,batch", [(synth.COCO416, 8), (SMALL, 3), (synth.SHIP608, 2)], ids=["coco416", "tiny", "ship608"])
+def test_two_part_loss_equals_one_call(cfg, batch):
+    """fvb_yolov3_loss_match_f32 (beside the decode) + fvb_yolov3_loss_finish_f32 (after it) == fvb_yolov3_loss_f32: same scalar,
+    fp64 partials equal up to the association of the sums, with labels and without."""
+    g = synth.make_generator(1)
+    labels = synth.make_labels(cfg, batch, g)
+    dh = [h.cuda() for h in synth.make_heads(cfg, batch, labels, g)]
+    step = ValStep(cfg.anchors_levels(), cfg.strides)
+    for dl in (labels.cuda(), labels[:1].cuda(), labels[:0].cuda()):
+        o = step(dh, dl)                                             # two-part form (ValStep._run)
+        torch.cuda.synchronize()
+        l2, p2 = o["loss"].clone(), o["partials"].clone()
+        step._decode(dh)
+        step._tail(dh, dl, reduce_inside=False, early_match=False)   # one-call form
+        torch.cuda.synchronize()
+        close(l2, o["loss"], rtol=2e-7, atol=0)
+        np.testing.assert_allclose(p2.cpu().numpy(), o["partials"].cpu().numpy(), rtol=1e-13, atol=0)
+
+
 def test_full_size_properties_b256():
     """BASELINE config 2 (B=256): size-independent properties instead of a full CPU oracle run."""
     cfg, batch = synth.COCO416, 256

@@ -41,14 +41,14 @@ for it in range(6):
     dist.barrier()
     torch.cuda.synchronize()
     ev["t0"].record(main)
-    step._head(dl)
     step._decode(dh)
     ev["decoded"].record(main)
     with torch.cuda.stream(side):
+        side.wait_event(ev["t0"])
+        step.loss_fn.match(dh, dl, ctx)              # beside the decode
         side.wait_event(ev["decoded"])
         ev["loss_begin"].record(side)
-        step.loss_fn(dh, dl, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"], prepared=step._prepared)
-        step._prepared = False
+        step.loss_fn.finish(dl.size(0), ctx, ctx.bce0(), out=o["loss"], partials=o["partials"])
         ev["loss_end"].record(side)
         step._reduce()
         ev["reduce_end"].record(side)
