@@ -45,10 +45,12 @@ def _base_from_anchor_xywh(anchor_xywh):
 
 
 def filter_proposals_batched(cls, dxdydwdh, anchor_xywh, rpn_pre_nms_top_n=2000, rpn_post_nms_top_n=2000,
-                             rpn_nms_thresh=0.7, want_idx=False):
+                             rpn_nms_thresh=0.7, want_idx=False, want_decoded=False):
     """cls [B,H,W,A,2], dxdydwdh [B,H,W,A,4] -> (xywh [B,post_n,4], cnt [B] int32[, anchor idx [B,post_n] int32]).
 
-    No host sync; entries past ``cnt[b]`` are undefined.
+    No host sync; entries past ``cnt[b]`` are undefined.  ``want_decoded`` (parity tests) appends the kernel's own
+    per-anchor results, copied out of the workspace: clamped xyxy boxes [B,n,4] and foreground scores [B,n] -- the
+    tensors the reference's ``topk -> nms`` (rpn.py:193-198) would be run on.
     """
     cls = _lib.require_cuda(cls, "cls")
     reg = _lib.require_cuda(dxdydwdh, "dxdydwdh")
@@ -70,9 +72,26 @@ def filter_proposals_batched(cls, dxdydwdh, anchor_xywh, rpn_pre_nms_top_n=2000,
         _lib.check(lib.fvb_rpn_proposals_f32(_lib.dptr(cls), _lib.dptr(reg), base_c, b, fh, fw, a, int(rpn_pre_nms_top_n),
                                              post, float(rpn_nms_thresh), _lib.dptr(out), _lib.dptr(idx), _lib.dptr(cnt),
                                              _lib.dptr(ws), _lib.stream()), "rpn_proposals")
-    if want_idx:
-        return out, cnt, idx
-    return out, cnt
+    res = (out, cnt, idx) if want_idx else (out, cnt)
+    if want_decoded:
+        res = res + _decoded_from_workspace(ws, b, fh * fw * a)
+    return res
+
+
+def _decoded_from_workspace(ws, b, n):
+    """Workspace layout of fvb_rpn_proposals_f32 (csrc/rpn.cu): 64-bit sort keys [B][2][n] (after the 4-pass sort the
+    ordered keys are back in the first half: high word = order-reversing image of the score bits, low word = anchor index),
+    then the clamped xyxy boxes [B][n] float4."""
+    align = lambda x: (x + 255) // 256 * 256
+    keys = ws[:b * 2 * n * 8].view(torch.int64).view(b, 2, n)[:, 0]
+    boxes = ws[align(b * 2 * n * 8):align(b * 2 * n * 8) + b * n * 16].view(torch.float32).view(b, n, 4).clone()
+    idx = keys & 0xffffffff
+    u = (~(keys >> 32)) & 0xffffffff                        # ascending-orderable image of the float (nms.cuh desc_key)
+    bits = torch.where((u & 0x80000000) != 0, u & 0x7fffffff, (~u) & 0xffffffff)
+    sc_sorted = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32).view(torch.float32)
+    scores = torch.empty(b, n, dtype=torch.float32, device=ws.device)
+    scores.scatter_(1, idx, sc_sorted)
+    return boxes, scores
 
 
 def filter_proposals(cls, dxdydwdh, anchor_xywh, feature_height=None, feature_width=None, rpn_pre_nms_top_n=2000,
