@@ -238,12 +238,13 @@ def run_cuda(args, cfg):
             cap_s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.graph(g_all, stream=cap_s):
                 for i in range(k):
+                    step._head(dh, dl)                     # loss_match on the side stream, beside the decode
                     if i in ev_d0:
                         ev_d0[i].record()
                     step._decode(dh)
                     if i in ev_d1:
                         ev_d1[i].record()
-                    step._tail(dh, dl, reduce_inside=distributed, early_match=True)   # loss_match beside the decode
+                    step._tail(dh, dl, reduce_inside=distributed)
             torch.cuda.current_stream().wait_stream(cap_s)
             g_all.replay()                      # one untimed replay (also validates the graph)
             torch.cuda.synchronize()

@@ -42,6 +42,8 @@ _SIGS = {
     "fvb_yolo_decode_partials": (C.c_int, [C.POINTER(Geom)]),
     "fvb_yolo_decode_workspace_bytes": (C.c_size_t, []),
     "fvb_yolo_decode_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), C.c_int, C.c_int, _P, C.c_float, _P, _P, _P, _P, _P]),
+    "fvb_yolo_decode_tiles_per_image": (C.c_int, [C.POINTER(Geom)]),
+    "fvb_yolo_decode_sync_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), C.c_int, C.c_int, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
     "fvb_box_convert_f32": (C.c_int, [_P, C.c_int64, C.c_int, C.c_float, C.c_float, _P, _P]),
     "fvb_iou_elementwise_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "fvb_iou_pairwise_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
@@ -53,6 +55,8 @@ _SIGS = {
     "fvb_yolo_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "fvb_yolo_nms_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_int, C.c_int, C.c_float,
                                    _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "fvb_yolo_nms_after_decode_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_double, C.c_int, C.c_int, C.c_float,
+                                                _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
     "fvb_rpn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fvb_rpn_proposals_f32": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_double, _P, _P, _P, _P, _P]),
@@ -60,6 +64,9 @@ _SIGS = {
     "fvb_yolov3_loss_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_float, C.c_float, C.c_float,
                                       _P, _P, _P, _P, _P]),
     "fvb_yolov3_loss_match_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, _P, _P]),
+    "fvb_yolov3_loss_dense_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                            _P, C.c_int, _P, _P, _P, _P]),
+    "fvb_yolov3_loss_match_dense_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_int, _P, _P]),
     "fvb_yolov3_loss_finish_f32": (C.c_int, [C.POINTER(Geom), C.c_int64, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     "fvb_yolov3_saved_conf_floats": (C.c_int64, [C.POINTER(Geom)]),
     "fvb_yolov3_loss_train_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), _P, C.c_int64, C.c_float, C.c_float, C.c_float,
@@ -90,7 +97,10 @@ _SIGS = {
     "fvb_map_ap_f64": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fvb_kmeans_workspace_bytes": (C.c_size_t, [C.c_int]),
     "fvb_kmeans_step_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
+    "fvb_debug_set_nms_trace": (None, [_P]),
+    "fvb_debug_reload_knobs": (None, []),
 }
+ABI_VERSION = 2
 
 EXPORTS = tuple(_SIGS)
 
@@ -115,8 +125,8 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the .so is stale: loud by design
             fn.restype = res
             fn.argtypes = args
-        if lib.fvb_abi_version() != 1:
-            raise RuntimeError("libfvb200.so ABI version %d, expected 1" % lib.fvb_abi_version())
+        if lib.fvb_abi_version() != ABI_VERSION:
+            raise RuntimeError("libfvb200.so ABI version %d, expected %d" % (lib.fvb_abi_version(), ABI_VERSION))
         _lib = lib
     return _lib
 
@@ -183,14 +193,37 @@ def head_ptrs(heads):
     return arr
 
 
-_ws_cache = {}
+class Workspaces:
+    """Scratch buffers owned by ONE object (a ValStep, a Yolov3Loss, a DecodeContext ...), one per tag and device.
+
+    A buffer that has to grow is RETIRED, not freed: a captured CUDA graph has the old pointer baked in and another
+    stream may still be using it, so handing the block back to the caching allocator would let a later tensor alias
+    memory that a ``graph.replay()`` still writes.  Retired buffers live as long as their owner; growth is geometric
+    (x1.5), so the memory held is bounded by ~3x the largest request.
+    """
+
+    def __init__(self):
+        self._bufs = {}
+        self._retired = []
+
+    def get(self, tag, nbytes, device, zero=False):
+        key = (tag, device.index if device.index is not None else torch.cuda.current_device())
+        buf = self._bufs.get(key)
+        nbytes = max(int(nbytes), 256)
+        if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                self._retired.append(buf)
+                nbytes = max(nbytes, buf.numel() * 3 // 2)
+            buf = (torch.zeros if zero else torch.empty)(nbytes, dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+_shared = Workspaces()
 
 
 def workspace(nbytes, device, tag="default"):
-    """A cached uint8 scratch tensor of at least nbytes on `device` (per tag, grows monotonically)."""
-    key = (tag, device.index if device.index is not None else torch.cuda.current_device())
-    buf = _ws_cache.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _ws_cache[key] = buf
-    return buf
+    """Process-wide scratch for the one-shot API calls (``non_max_suppression(x)``, ``cal_iou_batch`` ...): at least
+    ``nbytes`` of uint8 on ``device`` per tag.  Objects that capture CUDA graphs or run on their own streams (ValStep,
+    Yolov3Loss) own a private ``Workspaces`` instead of sharing these."""
+    return _shared.get(tag, nbytes, device)

@@ -48,7 +48,18 @@ struct DecodeParams {
   double* bce0;     // one zero-target objectness BCE partial per tile, level-major: [l][b][tile of the level]
   unsigned* sched;  // [0] next tile, [1] warps that have drained; both zero between launches
   int batch_max;    // tiles drawn per atomic while the queue is long
+  unsigned* tile_done;  // optional [B]: finished tiles per image, published with release semantics (consumer: yolo_nms_kernel
+                        // launched as a programmatic dependent, which starts an image's NMS while later images still decode)
 };
+
+// Publish `n` finished tiles of image b: every lane's stores of those tiles (results, candidate bits, records, objectness
+// partials) were ordered before this point by __syncwarp(); the gpu-scope fence + relaxed atomic by lane 0 is the release.
+__device__ __forceinline__ void publish_tiles(const DecodeParams& p, int b, int n, int lane) {
+  if (lane == 0 && n > 0) {
+    __threadfence();
+    atomicAdd(&p.tile_done[b], (unsigned)n);
+  }
+}
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -430,6 +441,11 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* buf = dec_smem + (size_t)warp * p.tile_floats;
   const int total = p.total_tiles;
+  // Programmatic dependent launch: the NMS kernel enqueued right behind this one may be scheduled as soon as every CTA of this
+  // grid has got here (i.e. IS RESIDENT -- which is what makes its spinning on tile_done[] deadlock-free); it does not wait for
+  // this grid to finish.  Without a dependent this is a no-op.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  int pend_b = -1, pend_n = 0;  // finished tiles of image pend_b not yet published
   // dynamic tile queue: tiles are handed out in memory order to whichever warp is free, so a CTA that starts late or
   // shares its SM with NMS CTAs of the previous batch simply takes fewer tiles.  A warp draws a BATCH of consecutive
   // tiles per atomic (same-address atomics serialise in one L2 slice: one per tile costs more than the tile), and the
@@ -468,6 +484,19 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
     __syncwarp();  // every lane's copies have landed
     process_tile<NSB, FORM, PRECISE>(p, cur, buf);
     __syncwarp();  // the buffer may be refilled
+    if (p.tile_done != nullptr) {
+      // one publication per image per drawn batch (a batch is <= batch_max consecutive tiles, mostly of one image)
+      if (cur.b != pend_b) {
+        publish_tiles(p, pend_b, pend_n, lane);
+        pend_b = cur.b;
+        pend_n = 0;
+      }
+      ++pend_n;
+      if (u + 1 >= uend) {
+        publish_tiles(p, pend_b, pend_n, lane);
+        pend_n = 0;
+      }
+    }
     if (fetch) {
       nu = __shfl_sync(0xffffffffu, t0, 0);
       nend = min(nu + g, total);
@@ -487,12 +516,21 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
   }
 }
 
-// Tuning knobs (environment, read once): warps per CTA, shared-memory stages per warp, rows per tile.
-static int knob(const char* name, int dflt, int lo, int hi) {
+// Tuning knobs (environment; each is read ONCE per process, at the first launch): warps per CTA, tiles drawn per ticket.
+static int read_knob(const char* name, int dflt, int lo, int hi) {
   const char* v = getenv(name);
   if (!v || !*v) return dflt;
   const int x = atoi(v);
   return x < lo ? lo : (x > hi ? hi : x);
+}
+static int g_knob_warps = -1, g_knob_batch = -1;  // -1 = not read yet (benign race: every reader computes the same value)
+static int knob_warps() {
+  if (g_knob_warps < 0) g_knob_warps = read_knob("FVB_DECODE_WARPS", 0, 0, kDecodeMaxThreads / 32);  // 0 = built-in defaults
+  return g_knob_warps;
+}
+static int knob_batch() {
+  if (g_knob_batch < 0) g_knob_batch = read_knob("FVB_DECODE_BATCH", 8, 1, 64);
+  return g_knob_batch;
 }
 
 // Launch shape shared by the decode entry point and by the loss (which sums the per-warp partials).
@@ -524,7 +562,7 @@ int decode_launch_shape(const Geom& g, DecodeShape* s) {
   int wpc = (int)(kDecodeSmemBudget / per_warp);
   // narrow rows (K <= 21: 64-128 rows, < 8 KB per tile) carry more per-row work per byte: 24 warps hide it better (608 / C=10 /
   // B=1024 with all side outputs: 0.557 ms at 20 warps, 0.512 at 24, 0.508 at 28); wide rows are best at 20 (0.304 vs 0.306 ms)
-  const int want = knob("FVB_DECODE_WARPS", s->tile_rows >= 64 ? 24 : kDecodeWarps, 1, kDecodeMaxThreads / 32);
+  const int want = knob_warps() ? knob_warps() : (s->tile_rows >= 64 ? 24 : kDecodeWarps);
   if (wpc > want) wpc = want;
   if (wpc < 1) {
     set_error("decode: K=%d rows do not fit the shared-memory tile", g.K);
@@ -628,9 +666,28 @@ extern "C" int fvb_yolo_decode_partials(const fvb_yolo_geom* geom) {
 
 extern "C" size_t fvb_yolo_decode_workspace_bytes(void) { return 256; }
 
+/* debug hook (tools/decode_sweep.py): forget the cached FVB_DECODE_* knobs so the next launch re-reads the environment */
+extern "C" void fvb_debug_reload_knobs(void) { g_knob_warps = g_knob_batch = -1; }
+
+extern "C" int fvb_yolo_decode_tiles_per_image(const fvb_yolo_geom* geom) {
+  Geom g;
+  if (make_geom(geom, nullptr, &g) != FVB_OK) return -1;
+  int t = 0;
+  const int tr = decode_tile_rows(g.K);
+  for (int l = 0; l < g.L; ++l) t += (g.A * g.HW[l] + tr - 1) / tr;
+  return t;
+}
+
 extern "C" int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
                                    float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
                                    double* d_conf_bce0, void* d_ws, void* stream) {
+  return fvb_yolo_decode_sync_f32(geom, d_heads, form, precise, d_results, conf_thr, d_cand_bitmap, d_cand_rec, d_conf_bce0,
+                                  nullptr, d_ws, stream);
+}
+
+extern "C" int fvb_yolo_decode_sync_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
+                                        float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
+                                        double* d_conf_bce0, uint32_t* d_tile_sync, void* d_ws, void* stream) {
   DecodeParams p;
   FVB_REQUIRE(d_heads != nullptr && d_results != nullptr && d_ws != nullptr, "decode: NULL head/result/workspace pointer");
   int rc = make_geom(geom, d_heads, &p.g);
@@ -670,7 +727,9 @@ extern "C" int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const
   p.bce0 = d_conf_bce0;
   p.cand_rec = d_cand_rec;
   p.sched = (unsigned*)d_ws;
-  p.batch_max = knob("FVB_DECODE_BATCH", 8, 1, 64);
+  p.tile_done = d_tile_sync;
+  FVB_REQUIRE(((uintptr_t)d_tile_sync & 3) == 0, "decode: tile_sync misaligned");
+  p.batch_max = knob_batch();
   cudaStream_t s = (cudaStream_t)stream;
   if (form == FVB_DECODE_V3) rc = precise ? launch_decode<FVB_DECODE_V3, true>(p, sh, s) : launch_decode<FVB_DECODE_V3, false>(p, sh, s);
   else rc = precise ? launch_decode<FVB_DECODE_V5, true>(p, sh, s) : launch_decode<FVB_DECODE_V5, false>(p, sh, s);

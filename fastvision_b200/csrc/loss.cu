@@ -30,6 +30,7 @@ struct LossParams {
   const double* conf0;               // zero-target objectness partials (decode tiles or conf_stream chunks), level-major
   int conf_begin[FVB_MAX_LEVELS];    // each level's contiguous range; CTA x of level l folds slice x of it into its sums
   int conf_end[FVB_MAX_LEVELS];
+  int dense_precise;                 // the dense zero-target partials were formed with the PRECISE sigmoid (decode precise=1)
 };
 
 __global__ void loss_prep_kernel(const float* labels, int T, int* flags) {
@@ -113,7 +114,9 @@ __global__ void __launch_bounds__(kLossThreads) loss_match_kernel(const LossPara
       if (!loser) {
         // the dense zero-target sum (decode tiles / conf_stream) holds bce(sigmoid_fast(t4), 0) for this cell: take
         // exactly that back out and put the true term in
-        r_conf = (double)bce_term(sigmoid_precise(r4), iou) - (double)bce_term_zero(sigmoid_fast(r4));
+        // (the same sigmoid form the producer of the dense sum used -- for large objectness logits 1 ulp of p is ~20 % of the term)
+        const float p_dense = p.dense_precise ? sigmoid_precise(r4) : sigmoid_fast(r4);
+        r_conf = (double)bce_term(sigmoid_precise(r4), iou) - (double)bce_term_zero(p_dense);
       }
       r_cls = s_cls;
       r_box = (double)(1.0f - ciou);
@@ -447,7 +450,7 @@ enum { kLossAll = 0, kLossMatchOnly = 1, kLossFinishOnly = 2 };
 static int run_yolov3_loss(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
                            int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
                            const double* d_conf_bce0, double* d_partials, float* d_out_loss,
-                           float* d_saved_conf, void* d_ws, void* stream, int mode) {
+                           float* d_saved_conf, void* d_ws, void* stream, int mode, int dense_precise = 0) {
   FVB_REQUIRE(d_ws != nullptr, "yolov3_loss: NULL workspace");
   FVB_REQUIRE(mode == kLossMatchOnly || d_partials != nullptr, "yolov3_loss: NULL partials");
   FVB_REQUIRE(mode == kLossFinishOnly || d_heads != nullptr, "yolov3_loss: NULL heads");
@@ -476,6 +479,8 @@ static int run_yolov3_loss(const fvb_yolo_geom* geom, const float* const* d_head
   double* finish_slices = (double*)(w + o);
   lp.labels = d_labels;
   lp.T = (int)num_labels;
+  // only partials that came from fvb_yolo_decode_f32(precise=1) are "precise"; conf_stream_kernel uses the MUFU sigmoid
+  lp.dense_precise = (dense_precise != 0 && (mode == kLossMatchOnly || (d_conf_bce0 != nullptr && d_saved_conf == nullptr))) ? 1 : 0;
 
   FinalizeParams fp;
   fp.g = g;
@@ -567,6 +572,21 @@ extern "C" int fvb_yolov3_loss_match_f32(const fvb_yolo_geom* geom, const float*
                                          int64_t num_labels, void* d_ws, void* stream) {
   return run_yolov3_loss(geom, d_heads, d_labels, num_labels, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, d_ws, stream,
                          kLossMatchOnly);
+}
+
+/* v2: the same two entry points for objectness partials produced by fvb_yolo_decode_f32(..., precise = 1) */
+extern "C" int fvb_yolov3_loss_dense_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                         int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                                         const double* d_conf_bce0, int conf_bce0_precise, double* d_partials,
+                                         float* d_out_loss, void* d_ws, void* stream) {
+  return run_yolov3_loss(geom, d_heads, d_labels, num_labels, ratio_box, ratio_conf, ratio_cls, d_conf_bce0, d_partials,
+                         d_out_loss, nullptr, d_ws, stream, kLossAll, conf_bce0_precise);
+}
+
+extern "C" int fvb_yolov3_loss_match_dense_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                               int64_t num_labels, int conf_bce0_precise, void* d_ws, void* stream) {
+  return run_yolov3_loss(geom, d_heads, d_labels, num_labels, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, d_ws, stream,
+                         kLossMatchOnly, conf_bce0_precise);
 }
 
 extern "C" int fvb_yolov3_loss_finish_f32(const fvb_yolo_geom* geom, int64_t num_labels, float ratio_box, float ratio_conf,

@@ -49,7 +49,16 @@ struct YoloNmsParams {
   float4* ws_box;               // [B][N]
   int* ws_row;                  // [B][N]
   long long* trace;             // debug: [B][8] clock64 stamps per phase (NULL in production)
+  // Programmatic-dependent form (fvb_yolo_nms_after_decode_f32): the grid starts while the decode kernel still runs.
+  unsigned* tile_sync;          // [B] finished tiles per image (published by decode_kernel), [B] = this grid's exit counter; or NULL
+  unsigned tiles_per_image;
 };
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 struct NmsSmemLayout {
   size_t keys0, box, row, cnt, warp_tot, kbox, karea, kslot, gs, misc, total;
@@ -78,10 +87,8 @@ __host__ __device__ inline NmsSmemLayout nms_layout(int cap, int max_keep) {
   return L;
 }
 
-__global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsParams p) {
-  extern __shared__ __align__(16) unsigned char smem[];
+__device__ __forceinline__ void yolo_nms_image(const YoloNmsParams& p, const int b, unsigned char* smem) {
   const NmsSmemLayout L = nms_layout(kCapS, p.max_det);
-  const int b = blockIdx.x;
   const int lane = threadIdx.x & 31;
   uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L.cnt);
   uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + L.warp_tot);
@@ -200,6 +207,49 @@ __global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsPara
   }
   if (threadIdx.x == 0) p.out_cnt[b] = kept;
   if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 5] = gtime_ns();
+}
+
+// One CTA per image.  PDL = launched as a programmatic dependent of decode_kernel (which has executed
+// griddepcontrol.launch_dependents in every CTA, i.e. all of its CTAs are resident and make progress on their own): the CTA
+// waits until its image's tiles are all published -- one thread polls with an acquire load, the others sleep in the
+// barrier -- and then runs the image's NMS while the decode kernel is still streaming the later images.  Only the images
+// decoded last are left when the decode kernel exits, so the step's tail is one image's NMS latency instead of a whole wave's.
+template <bool PDL>
+__global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int b = blockIdx.x;
+  bool ok = true;
+  if (PDL) {
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+      const long long t0 = gtime_ns();
+      int good = 1;
+      while (ld_acquire_gpu(&p.tile_sync[b]) < p.tiles_per_image) {
+        __nanosleep(256);
+        if (gtime_ns() - t0 > 4000000000ll) {  // 4 s: the producer is not running (misuse) -- report instead of hanging the GPU
+          good = 0;
+          break;
+        }
+      }
+      p.tile_sync[b] = 0u;  // re-armed for the next decode launch (stream-ordered after this grid)
+      s_ok = good;
+    }
+    __syncthreads();  // (cumulativity: thread 0's acquire + this barrier order every thread's reads after the decode's writes)
+    ok = s_ok != 0;
+  }
+  if (ok) yolo_nms_image(p, b, smem);
+  else if (threadIdx.x == 0) p.out_cnt[b] = -1;
+  if (PDL) {
+    // The grid after this one in the stream must not start before the DECODE grid has fully exited (it re-arms its tile queue
+    // last): the last CTA to leave waits for the prerequisite grid's completion, so this grid's completion implies it.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (atomicAdd(&p.tile_sync[p.B], 1u) == (unsigned)p.B - 1u) {
+        p.tile_sync[p.B] = 0u;
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+      }
+    }
+  }
 }
 
 // ---- stand-alone scoring: candidate bitmap + records straight from a decoded [B,N,K] tensor ------------------
@@ -341,8 +391,10 @@ static int ensure_smem(const void* fn, size_t bytes, const char* what) {
 
 using namespace fvb;
 
+// Debug hook (tools/nms_trace.py; declared in the "debug hooks" section of fvb200.h): device buffer [B][8] of globaltimer stamps
+// written by yolo_nms_kernel.  Process-global and NOT thread-safe by design -- the one piece of mutable state outside the
+// thread-local error string; NULL (the default) disables it and production code never sets it.
 static long long* g_nms_trace = nullptr;
-/* debug hook (tools/nms_trace.py): device buffer [B][8] of clock64 stamps written by yolo_nms_kernel; NULL disables */
 extern "C" void fvb_debug_set_nms_trace(void* d_buf) { g_nms_trace = (long long*)d_buf; }
 
 extern "C" size_t fvb_yolo_nms_workspace_bytes(int batch, int rows_per_image) {
@@ -361,6 +413,16 @@ extern "C" int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_
                                 double iou_thr, int max_det, int flavour, float max_wh, uint32_t* d_cand_bitmap,
                                 const float* d_cand_rec, int clear_bitmap, float* d_out_boxes, float* d_out_scores, int64_t* d_out_cls,
                                 int32_t* d_out_rows, int32_t* d_out_cnt, void* d_ws, void* stream) {
+  return fvb_yolo_nms_after_decode_f32(d_results, batch, rows_per_image, channels, conf_thr, iou_thr, max_det, flavour, max_wh,
+                                       d_cand_bitmap, d_cand_rec, clear_bitmap, d_out_boxes, d_out_scores, d_out_cls, d_out_rows,
+                                       d_out_cnt, nullptr, 0, d_ws, stream);
+}
+
+extern "C" int fvb_yolo_nms_after_decode_f32(const float* d_results, int batch, int rows_per_image, int channels, float conf_thr,
+                                             double iou_thr, int max_det, int flavour, float max_wh, uint32_t* d_cand_bitmap,
+                                             const float* d_cand_rec, int clear_bitmap, float* d_out_boxes, float* d_out_scores,
+                                             int64_t* d_out_cls, int32_t* d_out_rows, int32_t* d_out_cnt, uint32_t* d_tile_sync,
+                                             int tiles_per_image, void* d_ws, void* stream) {
   FVB_REQUIRE(batch >= 0 && batch <= 65535 && rows_per_image >= 1 && channels >= 6, "yolo_nms: bad shape B=%d N=%d K=%d", batch, rows_per_image, channels);
   FVB_REQUIRE(max_det >= 1, "yolo_nms: max_det=%d", max_det);
   FVB_REQUIRE(flavour >= FVB_NMS_LIB && flavour <= FVB_NMS_DEMO_BATCH, "yolo_nms: unknown flavour %d", flavour);
@@ -386,6 +448,8 @@ extern "C" int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_
   p.ws_box = (float4*)(w + o);              o = align_up(o + bn * 16, 256);
   p.ws_row = (int*)(w + o);                 o = align_up(o + bn * 4, 256);
   FVB_REQUIRE((d_cand_bitmap == nullptr) == (d_cand_rec == nullptr), "yolo_nms: pass both the candidate bitmap and the records, or neither");
+  FVB_REQUIRE(d_tile_sync == nullptr || (d_cand_bitmap != nullptr && tiles_per_image >= 1 && ((uintptr_t)d_tile_sync & 3) == 0),
+              "yolo_nms_after_decode: needs the decode's candidate bitmap/records and tiles_per_image >= 1");
   cudaStream_t cs = (cudaStream_t)stream;
   if (d_cand_bitmap) {
     p.bitmap = d_cand_bitmap;
@@ -416,12 +480,36 @@ extern "C" int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_
   p.out_rows = d_out_rows;
   p.out_cnt = d_out_cnt;
   p.trace = g_nms_trace;
+  p.tile_sync = d_tile_sync;
+  p.tiles_per_image = (unsigned)tiles_per_image;
   NmsSmemLayout L = nms_layout(kCapS, max_det);
-  int rc = ensure_smem((const void*)yolo_nms_kernel, L.total, "yolo_nms");
+  if (d_tile_sync == nullptr) {
+    int rc = ensure_smem((const void*)yolo_nms_kernel<false>, L.total, "yolo_nms");
+    if (rc != FVB_OK) return rc;
+    yolo_nms_kernel<false><<<batch, kNmsThreads, L.total, cs>>>(p);
+    count_launch();
+    return check_launch("yolo_nms_kernel");
+  }
+  int rc = ensure_smem((const void*)yolo_nms_kernel<true>, L.total, "yolo_nms_after_decode");
   if (rc != FVB_OK) return rc;
-  yolo_nms_kernel<<<batch, kNmsThreads, L.total, cs>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)batch);
+  cfg.blockDim = dim3(kNmsThreads);
+  cfg.dynamicSmemBytes = L.total;
+  cfg.stream = cs;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, yolo_nms_kernel<true>, p);
+  if (e != cudaSuccess) {
+    set_error("yolo_nms_after_decode: launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return FVB_E_CUDA;
+  }
   count_launch();
-  return check_launch("yolo_nms_kernel");
+  return check_launch("yolo_nms_kernel<pdl>");
 }
 
 extern "C" size_t fvb_nms_segmented_workspace_bytes(int64_t total_boxes, int segments) {

@@ -56,6 +56,15 @@ class DecodeContext:
         self._bitmap = None
         self._bce0 = None
         self._rec = None
+        self._tile_sync = None
+        self.tiles_per_image = lib.fvb_yolo_decode_tiles_per_image(self.geom)
+
+    def tile_sync(self):
+        """[B+1] u32 hand-shake between ``fvb_yolo_decode_sync_f32`` and ``fvb_yolo_nms_after_decode_f32``: finished tiles per
+        image + the consumer grid's exit counter.  Zero once; every decode + NMS pair leaves it zero."""
+        if self._tile_sync is None:
+            self._tile_sync = torch.zeros(self.batch + 1, dtype=torch.int32, device=self.device)
+        return self._tile_sync
 
     def bitmap(self):
         if self._bitmap is None:  # zero once; the NMS kernel clears what it consumes
@@ -84,7 +93,7 @@ class DecodeContext:
 
 
 def yolov3_decode(head_out, anchors_per_level, strides, form="v3", precise=False, ctx=None, out=None,
-                  conf_thres=None, want_bce0=False, layout="bahwk", row_order="ayx"):
+                  conf_thres=None, want_bce0=False, layout="bahwk", row_order="ayx", tile_sync=None):
     """Decode raw heads (list of [B,A,H,W,K]) into ``results`` [B,N,K]  (yolov3.py:36-51).
 
     ``layout="nchw"`` takes the conv outputs [B,A*K,H,W] directly (demos/yolov3_huaweiShip/customize_service.py:437).
@@ -94,7 +103,8 @@ def yolov3_decode(head_out, anchors_per_level, strides, form="v3", precise=False
 
     With ``conf_thres`` the kernel also fills ``ctx.bitmap()`` / ``ctx.records()`` (NMS candidates and their
     score / class / box records); with ``want_bce0`` it fills ``ctx.bce0()`` (zero-target objectness BCE
-    partials for Yolov3Loss).
+    partials for Yolov3Loss).  ``tile_sync`` (``ctx.tile_sync()``): publish per-image progress for an NMS launch that
+    follows DIRECTLY on the same stream with the same tensor (``non_max_suppression_batched(..., tile_sync=...)``).
     """
     heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
     if ctx is None:
@@ -106,10 +116,10 @@ def yolov3_decode(head_out, anchors_per_level, strides, form="v3", precise=False
     rec = ctx.records() if conf_thres is not None else None
     bce0 = ctx.bce0() if want_bce0 else None
     with torch.cuda.device(ctx.device):
-        _lib.check(lib.fvb_yolo_decode_f32(ctx.geom, _lib.head_ptrs(heads), _lib.DECODE_FORMS[form], 1 if precise else 0,
-                                           _lib.dptr(out), float(conf_thres if conf_thres is not None else 0.0),
-                                           _lib.dptr(bitmap), _lib.dptr(rec), _lib.dptr(bce0), _lib.dptr(ctx.sched()),
-                                           _lib.stream()),
+        _lib.check(lib.fvb_yolo_decode_sync_f32(ctx.geom, _lib.head_ptrs(heads), _lib.DECODE_FORMS[form], 1 if precise else 0,
+                                                _lib.dptr(out), float(conf_thres if conf_thres is not None else 0.0),
+                                                _lib.dptr(bitmap), _lib.dptr(rec), _lib.dptr(bce0), _lib.dptr(tile_sync),
+                                                _lib.dptr(ctx.sched()), _lib.stream()),
                    "yolo_decode")
     if row_order == "yxa":
         parts, r0 = [], 0

@@ -12,12 +12,16 @@ from ... import _lib
 
 def non_max_suppression_batched(results, conf_thres=0.25, iou_thres=0.45, max_det=300, flavour="lib",
                                 cand_bitmap=None, cand_records=None, clear_bitmap=True, max_wh=4096.0,
-                                want_rows=False, out=None):
+                                want_rows=False, out=None, tile_sync=None, tiles_per_image=0, ws=None):
     """results [B,N,K] decoded -> (boxes[B,max_det,4] xyxy, scores[B,max_det], cls[B,max_det] i64, cnt[B] i32[, rows]).
 
     Entries past cnt[b] are undefined.  ``cand_bitmap`` / ``cand_records`` are the [B, ceil(N/32)] int32 bitmap
     and [B,N,8] records written by the decode kernel for the same ``conf_thres`` (``DecodeContext.bitmap()`` /
     ``.records()``); without them one extra scoring launch derives both from ``results``.
+    ``tile_sync`` / ``tiles_per_image`` (``DecodeContext.tile_sync()`` / ``.tiles_per_image``): this call follows the
+    ``yolov3_decode(..., tile_sync=...)`` launch of the same tensors DIRECTLY on the current stream and is launched as its
+    programmatic dependent -- image b's NMS starts as soon as image b is decoded (``fvb_yolo_nms_after_decode_f32``).
+    ``ws``: caller-owned workspace (uint8, >= ``fvb_yolo_nms_workspace_bytes``) instead of the process-wide scratch.
     """
     results = _lib.require_cuda(results, "results")
     if results.dim() != 3:
@@ -33,12 +37,18 @@ def non_max_suppression_batched(results, conf_thres=0.25, iou_thres=0.45, max_de
     else:
         boxes, scores, cls, cnt, rows = out
     lib = _lib.load()
-    ws = _lib.workspace(lib.fvb_yolo_nms_workspace_bytes(b, n), dev, "yolo_nms")
+    need = lib.fvb_yolo_nms_workspace_bytes(b, n)
+    if ws is None:
+        ws = _lib.workspace(need, dev, "yolo_nms")
+    elif ws.numel() < need:
+        raise ValueError("yolo_nms workspace of %d bytes, need %d" % (ws.numel(), need))
     with torch.cuda.device(dev):
-        _lib.check(lib.fvb_yolo_nms_f32(_lib.dptr(results), b, n, k, float(conf_thres), float(iou_thres), int(max_det),
-                                        _lib.NMS_FLAVOURS[flavour], float(max_wh), _lib.dptr(cand_bitmap),
-                                        _lib.dptr(cand_records), 1 if clear_bitmap else 0, _lib.dptr(boxes), _lib.dptr(scores), _lib.dptr(cls),
-                                        _lib.dptr(rows), _lib.dptr(cnt), _lib.dptr(ws), _lib.stream()), "yolo_nms")
+        _lib.check(lib.fvb_yolo_nms_after_decode_f32(_lib.dptr(results), b, n, k, float(conf_thres), float(iou_thres), int(max_det),
+                                                     _lib.NMS_FLAVOURS[flavour], float(max_wh), _lib.dptr(cand_bitmap),
+                                                     _lib.dptr(cand_records), 1 if clear_bitmap else 0, _lib.dptr(boxes),
+                                                     _lib.dptr(scores), _lib.dptr(cls), _lib.dptr(rows), _lib.dptr(cnt),
+                                                     _lib.dptr(tile_sync), int(tiles_per_image) if tile_sync is not None else 0,
+                                                     _lib.dptr(ws), _lib.stream()), "yolo_nms")
     if want_rows:
         return boxes, scores, cls, cnt, rows
     return boxes, scores, cls, cnt

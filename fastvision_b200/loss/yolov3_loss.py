@@ -51,6 +51,7 @@ class Yolov3Loss(nn.Module):
         self.ratio_cls = ratio_cls
         self._ctx = None
         self.partials = None
+        self._ws = _lib.Workspaces()      # owned: a captured graph / side stream of this module keeps using its pointers
 
     def _context(self, y_pred):
         key = (y_pred[0].size(0), y_pred[0].size(1), y_pred[0].size(4), tuple(int(h.size(2)) for h in y_pred),
@@ -59,17 +60,18 @@ class Yolov3Loss(nn.Module):
             self._ctx = DecodeContext(y_pred, self.anchor_levels, self.backbone_stride_levels)
         return self._ctx
 
-    def match(self, y_pred, y_true, ctx):
+    def match(self, y_pred, y_true, ctx, conf_bce0_precise=False):
         """First part of the two-part inference form (fvb_yolov3_loss_match_f32): target assignment and matched-row terms from
         the RAW heads and the labels, enqueued on the current stream -- a caller that also decodes these heads (ValStep) runs
         it beside the decode.  ``finish`` completes the loss once the decode's objectness partials exist."""
         heads = [_lib.require_cuda(h.detach(), "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
         labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
         lib = _lib.load()
-        ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, labels.size(0)), ctx.device, "yolov3_loss")
+        ws = self._ws.get("yolov3_loss", lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, labels.size(0)), ctx.device)
         with torch.cuda.device(ctx.device):
-            _lib.check(lib.fvb_yolov3_loss_match_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), labels.size(0),
-                                                     _lib.dptr(ws), _lib.stream()), "yolov3_loss_match")
+            _lib.check(lib.fvb_yolov3_loss_match_dense_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), labels.size(0),
+                                                           1 if conf_bce0_precise else 0, _lib.dptr(ws), _lib.stream()),
+                       "yolov3_loss_match")
 
     def finish(self, num_labels, ctx, conf_bce0, out=None, partials=None):
         """Second part (fvb_yolov3_loss_finish_f32), after ``match`` and the decode on the same stream order."""
@@ -79,7 +81,7 @@ class Yolov3Loss(nn.Module):
         if partials is None:
             partials = torch.empty(ctx.geom.levels, 4, dtype=torch.float64, device=dev)
         lib = _lib.load()
-        ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, int(num_labels)), dev, "yolov3_loss")
+        ws = self._ws.get("yolov3_loss", lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, int(num_labels)), dev)
         with torch.cuda.device(dev):
             _lib.check(lib.fvb_yolov3_loss_finish_f32(ctx.geom, int(num_labels), float(self.ratio_box), float(self.ratio_conf),
                                                       float(self.ratio_cls), _lib.dptr(conf_bce0), _lib.dptr(partials),
@@ -87,20 +89,21 @@ class Yolov3Loss(nn.Module):
         self.partials = partials
         return out
 
-    def forward(self, y_pred, y_true, conf_bce0=None, ctx=None, out=None, partials=None):
+    def forward(self, y_pred, y_true, conf_bce0=None, ctx=None, out=None, partials=None, conf_bce0_precise=False):
         """y_pred: list of raw [B,A,H,W,K]; y_true [T,6] = [batch_idx, cls, xc, yc, w, h] -> Tensor[1].
 
         ``conf_bce0``: partials written by ``yolov3_decode(..., want_bce0=True)`` over the same heads; when
-        given the loss does not touch the dense objectness channel again.
+        given the loss does not touch the dense objectness channel again (``conf_bce0_precise``: that decode ran with
+        ``precise=True``).
         """
         heads = [_lib.require_cuda(h, "y_pred[%d]" % i) for i, h in enumerate(y_pred)]
         labels = _lib.require_cuda(y_true, "y_true").view(-1, 6)
         ctx = ctx or self._context(heads)
         if torch.is_grad_enabled() and any(h.requires_grad for h in heads):
             return _Yolov3LossFn.apply(self, labels.detach(), ctx, conf_bce0, out, partials, None, *heads)
-        return self._forward_impl(heads, labels, ctx, conf_bce0, out, partials)
+        return self._forward_impl(heads, labels, ctx, conf_bce0, out, partials, conf_bce0_precise=conf_bce0_precise)
 
-    def _forward_impl(self, heads, labels, ctx, conf_bce0, out, partials, saved_conf=None):
+    def _forward_impl(self, heads, labels, ctx, conf_bce0, out, partials, saved_conf=None, conf_bce0_precise=False):
         dev = ctx.device
         t = labels.size(0)
         if out is None:
@@ -108,8 +111,15 @@ class Yolov3Loss(nn.Module):
         if partials is None:
             partials = torch.empty(ctx.geom.levels, 4, dtype=torch.float64, device=dev)
         lib = _lib.load()
-        ws = _lib.workspace(lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, t), dev, "yolov3_loss")
+        ws = self._ws.get("yolov3_loss", lib.fvb_yolov3_loss_workspace_bytes(ctx.geom, t), dev)
         with torch.cuda.device(dev):
+            if conf_bce0 is not None and conf_bce0_precise and saved_conf is None:
+                _lib.check(lib.fvb_yolov3_loss_dense_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
+                                                         float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
+                                                         _lib.dptr(conf_bce0), 1, _lib.dptr(partials), _lib.dptr(out),
+                                                         _lib.dptr(ws), _lib.stream()), "yolov3_loss")
+                self.partials = partials
+                return out
             _lib.check(lib.fvb_yolov3_loss_train_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), t,
                                                      float(self.ratio_box), float(self.ratio_conf), float(self.ratio_cls),
                                                      _lib.dptr(conf_bce0), _lib.dptr(partials), _lib.dptr(out),
@@ -137,7 +147,7 @@ class Yolov3Loss(nn.Module):
         if grad_out is not None:
             grad_out = _lib.require_cuda(grad_out.detach().reshape(-1)[:1], "grad_out")
         lib = _lib.load()
-        ws = _lib.workspace(lib.fvb_yolov3_loss_backward_workspace_bytes(ctx.geom, labels.size(0)), dev, "yolov3_loss_bwd")
+        ws = self._ws.get("yolov3_loss_bwd", lib.fvb_yolov3_loss_backward_workspace_bytes(ctx.geom, labels.size(0)), dev)
         bg = int(batch_global) if batch_global else int(heads[0].size(0))
         with torch.cuda.device(dev):
             _lib.check(lib.fvb_yolov3_loss_backward_f32(ctx.geom, _lib.head_ptrs(heads), _lib.dptr(labels), labels.size(0),

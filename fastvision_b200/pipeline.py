@@ -2,10 +2,12 @@
 reference's ``Fit._val`` (utils/fit.py:86-95) without its per-image Python loop and host syncs.
 
 Kernel sequence per step (5 launches, optionally replayed as one CUDA graph):
-    decode (+ NMS candidate bitmap/records + zero-target objectness BCE partials)   fvb_yolo_decode_f32
-    then two independent branches:
-      NMS for every image                                                          fvb_yolo_nms_f32
-      loss_prep, loss_match, loss_finalize (second stream)                         fvb_yolov3_loss_f32
+    side stream   loss_prep, loss_match (raw heads + labels only: beside the decode)             fvb_yolov3_loss_match_dense_f32
+    main stream   decode (+ NMS candidate bitmap/records + zero-target objectness BCE partials,
+                  publishing per-image progress)                                                 fvb_yolo_decode_sync_f32
+    main stream   NMS for every image, a PROGRAMMATIC DEPENDENT of the decode kernel: image b's
+                  CTA starts when image b is decoded, while later images still stream            fvb_yolo_nms_after_decode_f32
+    side stream   after the decode: objectness-partials sum + reduce (+ data-parallel combine)    fvb_yolov3_loss_finish_f32
 Under ``torch.distributed`` the batch is sharded per image: every rank runs the same step on its slice
 and the only collective is an all-reduce of the L*4 fp64 loss partials; decode and NMS need none.
 """
@@ -28,7 +30,7 @@ class _ModelStub:
 class ValStep:
     def __init__(self, anchors_per_level, strides, conf_thres=0.25, iou_thres=0.45, max_det=300,
                  ratio_box=0.05, ratio_conf=1.0, ratio_cls=0.5, nms_flavour="lib", precise_decode=False,
-                 process_group=None, batch_global: Optional[int] = None):
+                 process_group=None, batch_global: Optional[int] = None, overlap_nms=True):
         self.anchors_per_level = anchors_per_level
         self.strides = strides
         self.conf_thres, self.iou_thres, self.max_det = conf_thres, iou_thres, max_det
@@ -44,6 +46,10 @@ class ValStep:
         self._ev_decoded = None
         self._ev_loss = None
         self._peer_reducer = False       # not looked up yet
+        # image b's NMS starts as soon as image b is decoded: the NMS kernel is launched as a programmatic dependent of the
+        # decode kernel and follows its per-image progress counters (fvb_yolo_decode_sync_f32 / fvb_yolo_nms_after_decode_f32)
+        self.overlap_nms = overlap_nms
+        self._ws = _lib.Workspaces()     # owned by this step: a captured graph has these pointers baked in
 
     def _prepare(self, heads):
         ctx = DecodeContext(heads, self.anchors_per_level, self.strides)
@@ -64,6 +70,8 @@ class ValStep:
         ctx.bitmap()
         ctx.records()
         ctx.bce0()
+        ctx.tile_sync()
+        self._nms_ws = self._ws.get("yolo_nms", _lib.load().fvb_yolo_nms_workspace_bytes(b, ctx.rows), dev)
         self.graph = None
         # NMS (latency-bound, one CTA per image) and the loss kernels only depend on the decode: they run as
         # two branches (second stream; two parallel branches of the graph when captured)
@@ -76,37 +84,44 @@ class ValStep:
         return self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                        and torch.distributed.get_world_size() > 1)
 
+    def _head(self, heads, labels):
+        """First launches of a step: the loss's target assignment + matched-row terms read only the RAW heads and the labels,
+        so they go onto the side stream BEFORE the decode is launched -- their few small CTAs take their SM slots first and
+        hide under the decode kernel (launched after the decode + overlapped NMS pair they would wait for free registers)."""
+        self._ev_start.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ev_start)
+            self.loss_fn.match(heads, labels, self.ctx, conf_bce0_precise=self.precise)
+
     def _decode(self, heads):
         ctx, o = self.ctx, self.out
-        self._ev_start.record(torch.cuda.current_stream())     # what the early half of the loss waits for (see _tail)
         yolov3_decode(heads, self.anchors_per_level, self.strides, precise=self.precise, ctx=ctx, out=o["results"],
-                      conf_thres=self.conf_thres, want_bce0=True)
+                      conf_thres=self.conf_thres, want_bce0=True, tile_sync=ctx.tile_sync() if self.overlap_nms else None)
 
-    def _tail(self, heads, labels, reduce_inside=False, early_match=False):
-        """Everything after the decode launch: the NMS branch and the loss branch (second stream), joined at the end.
-        ``reduce_inside`` puts the data-parallel all-reduce + combine into the loss branch.
-        ``early_match`` (only right after ``_decode`` in the same eager / captured sequence): the loss runs in its two-part
-        form -- target assignment and matched-row terms wait only for the step's START, so they run beside the decode kernel
-        (launched first) and hide under it; after the decode only the small objectness-partials sum + reduce remain, so the
-        loss branch is neither the step's tail on several GPUs nor a competitor of the NMS CTAs on one."""
+    def _nms(self):
+        """NMS of every image (main stream).  With ``overlap_nms`` this launch must directly follow ``_decode``'s."""
+        ctx, o = self.ctx, self.out
+        sync = ctx.tile_sync() if self.overlap_nms else None
+        non_max_suppression_batched(o["results"], self.conf_thres, self.iou_thres, self.max_det, self.nms_flavour,
+                                    cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=True,
+                                    out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]),
+                                    tile_sync=sync, tiles_per_image=ctx.tiles_per_image, ws=self._nms_ws)
+
+    def _tail(self, heads, labels, reduce_inside=False):
+        """Everything after the decode launch (``_head`` and ``_decode`` came first): the NMS kernel directly behind the decode
+        kernel on the main stream (its programmatic dependent: image b's NMS starts when image b is decoded), and on the side
+        stream the second half of the two-part loss -- the sum of the decode's objectness partials + the reduction of the
+        matched terms -- followed, with ``reduce_inside``, by the data-parallel all-reduce + combine.  Joined at the end."""
         ctx, o = self.ctx, self.out
         main = torch.cuda.current_stream()
-        self._ev_decoded.record(main)
+        self._ev_decoded.record(main)       # (an event record is not a launch: the NMS kernel still follows the decode kernel)
+        self._nms()
         with torch.cuda.stream(self._side):
-            if early_match:
-                self._side.wait_event(self._ev_start)
-                self.loss_fn.match(heads, labels, ctx)
-                self._side.wait_event(self._ev_decoded)
-                self.loss_fn.finish(labels.size(0), ctx, ctx.bce0(), out=o["loss"], partials=o["partials"])
-            else:
-                self._side.wait_event(self._ev_decoded)
-                self.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
+            self._side.wait_event(self._ev_decoded)
+            self.loss_fn.finish(labels.size(0), ctx, ctx.bce0(), out=o["loss"], partials=o["partials"])
             if reduce_inside:
                 self._reduce()
             self._ev_loss.record(self._side)
-        non_max_suppression_batched(o["results"], self.conf_thres, self.iou_thres, self.max_det, self.nms_flavour,
-                                    cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=True,
-                                    out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]))
         main.wait_event(self._ev_loss)
 
     def _reduce(self):
@@ -131,8 +146,9 @@ class ValStep:
         return self._peer_reducer
 
     def _run(self, heads, labels):
+        self._head(heads, labels)
         self._decode(heads)
-        self._tail(heads, labels, reduce_inside=True, early_match=True)
+        self._tail(heads, labels, reduce_inside=True)
         return self.out
 
     def __call__(self, head_out: List[torch.Tensor], labels: torch.Tensor):
@@ -150,7 +166,8 @@ class ValStep:
         """Capture the step for these (static) input tensors into a CUDA graph; returns a replay callable.
 
         With ``split_decode`` only the part after the decode is captured and ``(decode_fn, tail_replay)`` is
-        returned, so a caller can bracket the (eagerly launched) decode kernel with timing events.
+        returned, so a caller can bracket the (eagerly launched) decode kernel with timing events (the NMS kernel is then
+        not a programmatic dependent of the decode: it finds every image complete and runs as a plain launch would).
         """
         heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
         labels = _lib.require_cuda(labels, "labels").view(-1, 6)
@@ -160,7 +177,7 @@ class ValStep:
             if self._peer() is None:
                 # NCCL fallback: keep the all-reduce out of any graph and inside the loss branch (overlaps the NMS)
                 if split_decode:
-                    return (lambda: self._decode(heads)), (lambda: self._tail(heads, labels, reduce_inside=True))
+                    return (lambda: (self._head(heads, labels), self._decode(heads))), (lambda: self._tail(heads, labels, reduce_inside=True))
                 return lambda: self._run(heads, labels)
             dist_graph = True    # the peer-memory reduce is an ordinary kernel: the whole step can be captured
         warm = torch.cuda.Stream(device=self.ctx.device)
@@ -173,12 +190,13 @@ class ValStep:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             if not split_decode:
+                self._head(heads, labels)
                 self._decode(heads)
-            self._tail(heads, labels, reduce_inside=dist_graph, early_match=not split_decode)
+            self._tail(heads, labels, reduce_inside=dist_graph)
         self.graph = g
 
         if split_decode:
-            return (lambda: self._decode(heads)), g.replay
+            return (lambda: (self._head(heads, labels), self._decode(heads))), g.replay
         return g.replay
 
     def detections(self, out=None):
@@ -202,6 +220,7 @@ class ValPipeline:
     """
 
     def __init__(self, anchors_per_level, strides, depth=2, **kw):
+        kw = dict(kw, overlap_nms=False)     # decode and NMS sit on different streams here: plain (stream-ordered) launches
         self.steps = [ValStep(anchors_per_level, strides, **kw) for _ in range(depth)]
         self.depth = depth
         self.count = 0
@@ -254,7 +273,8 @@ class ValPipeline:
             loss_s.wait_event(ev_dec)
             if trace is not None:
                 trace["loss"][0].record(loss_s)
-            st.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"])
+            st.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"],
+                       conf_bce0_precise=st.precise)
             st._reduce()
             if trace is not None:
                 trace["loss"][1].record(loss_s)
@@ -263,9 +283,7 @@ class ValPipeline:
             nms_s.wait_event(ev_dec)
             if trace is not None:
                 trace["nms"][0].record(nms_s)
-            non_max_suppression_batched(o["results"], st.conf_thres, st.iou_thres, st.max_det, st.nms_flavour,
-                                        cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=True,
-                                        out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]))
+            st._nms()
             if trace is not None:
                 trace["nms"][1].record(nms_s)
             ev_nms.record(nms_s)

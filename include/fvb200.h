@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define FVB_ABI_VERSION 1
+#define FVB_ABI_VERSION 2 /* 2 = 1 + the *_sync / *_after_decode / *_dense entry points (additive: every v1 signature is unchanged) */
 #define FVB_MAX_LEVELS 4
 #define FVB_MAX_ANCHORS 16
 
@@ -112,6 +112,15 @@ size_t fvb_yolo_decode_workspace_bytes(void);
 int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
                         float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
                         double* d_conf_bce0, void* d_ws, void* stream);
+/* The same decode, additionally publishing its progress per image so that the per-image body of Fit._val (utils/fit.py:94-95:
+ * non_max_suppression of image i) can start while later images are still being decoded.  d_tile_sync: [B + 1] u32, ZERO
+ * before the first call; entry b counts the finished tiles of image b (release semantics: all of the image's results, candidate
+ * bits, records and objectness partials are visible once it reads fvb_yolo_decode_tiles_per_image(geom)); the consumer,
+ * fvb_yolo_nms_after_decode_f32, must be the NEXT launch on `stream` and leaves the array zero again.  NULL = plain decode. */
+int fvb_yolo_decode_tiles_per_image(const fvb_yolo_geom* geom);
+int fvb_yolo_decode_sync_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
+                             float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
+                             double* d_conf_bce0, uint32_t* d_tile_sync, void* d_ws, void* stream);
 
 /* ---- box conversion ------------------------------------------------------------------------
  * detection/tools/BOX.py:4-26.  op: 0 xywh2xyxy, 1 xyxy2xywh, 2 xyxy2xywhn (needs height,width).
@@ -177,6 +186,16 @@ int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_image, int 
                      double iou_thr, int max_det, int flavour, float max_wh, uint32_t* d_cand_bitmap,
                      const float* d_cand_rec, int clear_bitmap, float* d_out_boxes, float* d_out_scores, int64_t* d_out_cls,
                      int32_t* d_out_rows, int32_t* d_out_cnt, void* d_ws, void* stream);
+/* The same call as the consumer of fvb_yolo_decode_sync_f32 (same d_tile_sync, tiles_per_image =
+ * fvb_yolo_decode_tiles_per_image(geom), same d_cand_bitmap / d_cand_rec, enqueued directly behind it on the same stream): the
+ * kernel is launched as a PROGRAMMATIC DEPENDENT of the decode kernel, so image b's NMS starts as soon as image b is decoded
+ * and only the images decoded last remain when the decode kernel exits.  Results are identical to fvb_yolo_nms_f32.  If the
+ * decode launch is missing the kernel gives up after ~4 s and writes d_out_cnt[b] = -1 (it never hangs the device). */
+int fvb_yolo_nms_after_decode_f32(const float* d_results, int batch, int rows_per_image, int channels, float conf_thr,
+                                  double iou_thr, int max_det, int flavour, float max_wh, uint32_t* d_cand_bitmap,
+                                  const float* d_cand_rec, int clear_bitmap, float* d_out_boxes, float* d_out_scores,
+                                  int64_t* d_out_cls, int32_t* d_out_rows, int32_t* d_out_cnt, uint32_t* d_tile_sync,
+                                  int tiles_per_image, void* d_ws, void* stream);
 
 /* fvb_rpn_proposals_f32: RPN.filter_proposals, demos/faster_rcnn/models/rpn.py:168-208 (+ :111-119,
  * :160-166).  d_cls [B,H,W,A,2], d_reg [B,H,W,A,4], base_anchors (host) [A,2] (w,h) feature units.
@@ -213,6 +232,15 @@ int fvb_yolov3_loss_match_f32(const fvb_yolo_geom* geom, const float* const* d_h
 int fvb_yolov3_loss_finish_f32(const fvb_yolo_geom* geom, int64_t num_labels, float ratio_box, float ratio_conf,
                                float ratio_cls, const double* d_conf_bce0, double* d_partials, float* d_out_loss,
                                void* d_ws, void* stream);
+/* v2: forms for objectness partials that came from fvb_yolo_decode_f32(..., precise = 1): the matched cells then take the
+ * dense term back out with the same (precise) sigmoid the decode used -- for objectness logits above ~13 one ulp of p is
+ * ~20 % of -log(1 - p + 1e-8), so the two forms must agree bit for bit to cancel.  conf_bce0_precise = 0 is the v1 call. */
+int fvb_yolov3_loss_dense_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                              int64_t num_labels, float ratio_box, float ratio_conf, float ratio_cls,
+                              const double* d_conf_bce0, int conf_bce0_precise, double* d_partials, float* d_out_loss,
+                              void* d_ws, void* stream);
+int fvb_yolov3_loss_match_dense_f32(const fvb_yolo_geom* geom, const float* const* d_heads, const float* d_labels,
+                                    int64_t num_labels, int conf_bce0_precise, void* d_ws, void* stream);
 /* Training form of the same call: additionally writes d_saved_conf ([fvb_yolov3_saved_conf_floats(geom)] f32, may be
  * NULL), a compact level-major copy [l][b][row] of the objectness logits, which fvb_yolov3_loss_backward_f32 then reads
  * instead of striding through the heads again.  With d_saved_conf the call always streams channel 4 itself. */
@@ -325,6 +353,16 @@ int fvb_map_ap_f64(const float* d_dets, const uint8_t* d_correct, int64_t n_dets
 size_t fvb_kmeans_workspace_bytes(int k);
 int fvb_kmeans_step_f32(const float* d_samples, int64_t n, const float* d_centers, int k, float eps, int64_t* d_categories,
                         float* d_new_centers, void* d_ws, void* stream);
+
+/* ---- debug hooks -------------------------------------------------------------------------------
+ * NOT part of the product path and NOT thread-safe: process-global state, used by tools/ only.
+ *   fvb_debug_set_nms_trace   device buffer [B][8] int64 of globaltimer stamps per NMS phase written by the
+ *                             fvb_yolo_nms_* kernels (tools/nms_trace.py); NULL (default) disables it.
+ *   fvb_debug_reload_knobs    the FVB_DECODE_WARPS / FVB_DECODE_BATCH environment knobs are read once per
+ *                             process; this makes the next decode launch read them again (tools/decode_sweep.py).
+ */
+void fvb_debug_set_nms_trace(void* d_buf);
+void fvb_debug_reload_knobs(void);
 
 #ifdef __cplusplus
 }

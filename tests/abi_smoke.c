@@ -18,7 +18,7 @@ int main(void) {
     g.stride[l] = (float)(32 >> l);
   }
   g.head_layout = FVB_HEAD_BAHWK;
-  if (fvb_abi_version() != 1) return 1;
+  if (fvb_abi_version() != FVB_ABI_VERSION) return 1;
   if (fvb_yolo_rows_per_image(&g) != 10647) return 2;
   if (fvb_yolo_bitmap_words(&g) != 333) return 3;
   g.channels = 3; /* invalid: the error comes back as a code + message, not an exception */

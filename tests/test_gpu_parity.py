@@ -408,11 +408,12 @@ def test_two_part_loss_equals_one_call(cfg, batch):
         o = step(dh, dl)                                             # two-part form (ValStep._run)
         torch.cuda.synchronize()
         l2, p2 = o["loss"].clone(), o["partials"].clone()
-        step._decode(dh)
-        step._tail(dh, dl, reduce_inside=False, early_match=False)   # one-call form
+        step._decode(dh)                                             # one-call form on the same decode side outputs
+        step._nms()
+        l1 = step.loss_fn(dh, dl, conf_bce0=step.ctx.bce0(), ctx=step.ctx)
         torch.cuda.synchronize()
-        close(l2, o["loss"], rtol=2e-7, atol=0)
-        np.testing.assert_allclose(p2.cpu().numpy(), o["partials"].cpu().numpy(), rtol=1e-13, atol=0)
+        close(l2, l1, rtol=2e-7, atol=0)
+        np.testing.assert_allclose(p2.cpu().numpy(), step.loss_fn.partials.cpu().numpy(), rtol=1e-13, atol=0)
 
 
 def test_full_size_properties_b256():

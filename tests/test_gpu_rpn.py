@@ -2,8 +2,8 @@
 from the reference's RPN.filter_proposals and against the CPU oracle.
 
 Proposal boxes: rtol 1e-5 (fp32 exp / softmax).  Which anchors survive is an index result: exact, checked on the
-kernel's own decoded boxes/scores (oracle NMS re-run on them) so that 1-ulp score differences between the CPU and
-GPU exp cannot reorder near-tied anchors.
+kernel's own decoded boxes/scores (``want_decoded``: oracle topk + NMS re-run on them) so that 1-ulp score differences
+between the CPU and GPU exp cannot reorder near-tied anchors.
 """
 import numpy as np
 import pytest
@@ -61,35 +61,43 @@ def _decoded_on_cpu(cls, reg, base):
 
 @pytest.mark.parametrize("pre,post,thr", [(12000, 2000, 0.7), (6000, 300, 0.7), (2000, 2000, 0.7)])
 def test_rpn_config4_shape_vs_oracle(pre, post, thr):
-    """BASELINE config 4 geometry (50x50x9 = 22 500 anchors / image), 3 images through the oracle."""
+    """BASELINE config 4 geometry (50x50x9 = 22 500 anchors / image), 3 images.
+
+    Index parity is EXACT: the reference's per-image ``topk -> nms -> [:post]`` (rpn.py:193-203) is re-run by the oracle on the
+    KERNEL'S OWN decoded boxes and scores (so a 1-ulp difference between the CPU and GPU ``exp`` cannot reorder near-tied
+    anchors), and the anchor index lists must be identical -- the only excuse is an evaluated pair with |IoU - thr| < 1e-6
+    (north-star), which is computed, never assumed.  ``torch.topk`` leaves the order of equal scores unspecified; the kernel
+    ranks them by lower anchor index, which is what the oracle's stable sort does too."""
     gen = synth.make_generator(4)
     b, fh, fw, a = 3, 50, 50, 9
     cls, reg = synth.make_rpn_inputs(b, fh, fw, a, gen)
     base = ft.get_base_anchor([128, 256, 512], [1, 0.5, 2]) / 16
-    out, cnt, idx = ft.filter_proposals_batched(cls.cuda(), reg.cuda(), base, pre, post, thr, want_idx=True)
-    out, cnt, idx = out.cpu(), cnt.cpu(), idx.cpu().long()
+    out, cnt, idx, gbox, gsc = ft.filter_proposals_batched(cls.cuda(), reg.cuda(), base, pre, post, thr, want_idx=True,
+                                                           want_decoded=True)
+    out, cnt, idx, gbox, gsc = out.cpu(), cnt.cpu(), idx.cpu().long(), gbox.cpu(), gsc.cpu()
     xyxy, sc = _decoded_on_cpu(cls, reg, base)
+    # the kernel's decode against the oracle's (rpn.py:111-119,173-185): every anchor, fp32 tolerance
+    close(gbox, xyxy, rtol=1e-5, atol=1e-5)
+    close(gsc, sc, rtol=1e-5, atol=1e-7)
+    excused = 0
     for i in range(b):
         k = int(cnt[i])
         assert 0 < k <= post
-        # decode parity on the surviving anchors
-        kb = xyxy[i, idx[i, :k]]
-        want_xywh = torch.stack([(kb[:, 0] + kb[:, 2]) / 2, (kb[:, 1] + kb[:, 3]) / 2, kb[:, 2] - kb[:, 0], kb[:, 3] - kb[:, 1]], 1)
-        close(out[i, :k], want_xywh, rtol=1e-5, atol=1e-5)
-        # ranking: proposals come out score-descending (up to 1-ulp exp differences between CPU and GPU)
-        s = sc[i, idx[i, :k]]
-        assert bool((s[:-1] >= s[1:] - 1e-6).all())
-        # the reference's own answer: topk -> nms -> first post_n; identical anchor list unless a near-tie in
-        # score (<= 2e-7) or an IoU within 1e-6 of the threshold flipped a decision
-        want = orpn.filter_proposals(cls[i:i + 1], reg[i:i + 1], base, pre, post, thr)[0]
-        top = sc[i].topk(min(pre, sc.size(1)))[1]
-        keep = on.nms_greedy(xyxy[i, top], sc[i, top], thr)[:post]
-        want_idx = top[keep]
-        assert want.size(0) == want_idx.numel()
-        same = (want_idx.numel() == k) and bool((want_idx == idx[i, :k]).all())
+        order = torch.argsort(gsc[i], descending=True, stable=True)[:min(pre, gsc.size(1))]     # rpn.py:193-195
+        keep, margin = on.nms_greedy(gbox[i, order], gsc[i, order], thr, return_iou_margin=True)  # rpn.py:198
+        want_idx = order[keep[:post]]                                                           # rpn.py:201-203
+        same = want_idx.numel() == k and bool((want_idx == idx[i, :k]).all())
         if not same:
-            common = len(set(want_idx.tolist()) & set(idx[i, :k].tolist()))
-            assert common >= 0.995 * max(k, want_idx.numel()), (i, k, want_idx.numel(), common)
+            assert margin < 1e-6, (i, k, want_idx.numel(), margin)
+            excused += 1
+        # proposals are the xywh form of exactly those boxes (rpn.py:139-145)
+        kb = gbox[i, idx[i, :k]]
+        want_xywh = torch.stack([(kb[:, 0] + kb[:, 2]) / 2, (kb[:, 1] + kb[:, 3]) / 2, kb[:, 2] - kb[:, 0], kb[:, 3] - kb[:, 1]], 1)
+        assert torch.equal(out[i, :k], want_xywh)
+        # and the end-to-end answer of the oracle on its own CPU decode has the same length unless a near-tie flipped a decision
+        want = orpn.filter_proposals(cls[i:i + 1], reg[i:i + 1], base, pre, post, thr)[0]
+        assert abs(want.size(0) - k) <= max(2, k // 200)
+    print("rpn %d/%d: %d image(s) excused by |IoU-thr|<1e-6" % (pre, post, excused))
 
 
 def test_rpn_batch64_properties():

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "libfvb200.so does not export %s" % name
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
-    assert _lib.load().fvb_abi_version() == 1
+    assert _lib.load().fvb_abi_version() == 2
 
 
 def test_product_never_imports_the_oracle():

@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fastvision_b200 import synth  # noqa: E402
+from fastvision_b200 import synth, _lib  # noqa: E402
 from fastvision_b200.detection.models import yolov3_decode, DecodeContext  # noqa: E402
 from microbench import timeit  # noqa: E402
 
@@ -21,6 +21,7 @@ for warps, gb in [(16, 8), (16, 1), (16, 4), (16, 16), (20, 8), (16, 8), (12, 8)
     stages, tr = 1, gb
     os.environ["FVB_DECODE_BATCH"] = str(gb)
     os.environ["FVB_DECODE_WARPS"] = str(warps)
+    _lib.load().fvb_debug_reload_knobs()          # the library caches the knobs after its first launch
     ctx = DecodeContext(heads, anc, st)
     res = torch.empty(batch, ctx.rows, ctx.k, device="cuda")
     nbytes = 2 * batch * ctx.rows * ctx.k * 4

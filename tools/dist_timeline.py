@@ -41,20 +41,19 @@ for it in range(6):
     dist.barrier()
     torch.cuda.synchronize()
     ev["t0"].record(main)
-    step._decode(dh)
-    ev["decoded"].record(main)
     with torch.cuda.stream(side):
         side.wait_event(ev["t0"])
         step.loss_fn.match(dh, dl, ctx)              # beside the decode
+    step._decode(dh)
+    ev["decoded"].record(main)
+    with torch.cuda.stream(side):
         side.wait_event(ev["decoded"])
         ev["loss_begin"].record(side)
         step.loss_fn.finish(dl.size(0), ctx, ctx.bce0(), out=o["loss"], partials=o["partials"])
         ev["loss_end"].record(side)
         step._reduce()
         ev["reduce_end"].record(side)
-    non_max_suppression_batched(o["results"], step.conf_thres, step.iou_thres, step.max_det, step.nms_flavour,
-                                cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=True,
-                                out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]))
+    step._nms()
     ev["nms_end"].record(main)
     main.wait_event(ev["reduce_end"])
     torch.cuda.synchronize()
