@@ -55,6 +55,7 @@ struct DecodeShape {
   size_t smem_bytes;
 };
 int decode_launch_shape(const Geom& g, DecodeShape* s);
+long long* debug_trace_ptr();  // nms.cu: the buffer of fvb_debug_set_nms_trace (NULL unless a tool set it)
 int decode_tile_rows(int K);
 
 // host+device for the pure arithmetic: tests/host_check.cu runs the same source on the CPU (no GPU in the build container)

@@ -48,6 +48,7 @@ struct DecodeParams {
   double* bce0;     // one zero-target objectness BCE partial per tile, level-major: [l][b][tile of the level]
   unsigned* sched;  // [0] next tile, [1] warps that have drained; both zero between launches
   int batch_max;    // tiles drawn per atomic while the queue is long
+  long long* trace;     // debug (fvb_debug_set_nms_trace): [9 B] earliest CTA start, [9 B + 1] latest CTA end; NULL in production
   unsigned* tile_done;  // optional [B]: finished tiles per image, published with release semantics (consumer: yolo_nms_kernel
                         // launched as a programmatic dependent, which starts an image's NMS while later images still decode)
 };
@@ -445,7 +446,13 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
   // grid has got here (i.e. IS RESIDENT -- which is what makes its spinning on tile_done[] deadlock-free); it does not wait for
   // this grid to finish.  Without a dependent this is a no-op.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMin(p.trace + 9 * p.g.B, t);
+  }
   int pend_b = -1, pend_n = 0;  // finished tiles of image pend_b not yet published
+  int pub_n = 0;                // ... of which this many are due at the next opportunity
   // dynamic tile queue: tiles are handed out in memory order to whichever warp is free, so a CTA that starts late or
   // shares its SM with NMS CTAs of the previous batch simply takes fewer tiles.  A warp draws a BATCH of consecutive
   // tiles per atomic (same-address atomics serialise in one L2 slice: one per tile costs more than the tile), and the
@@ -473,6 +480,12 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
     if (p.g.nchw) issue_tile_nchw<NSB>(p, cur, buf, lane);
     else issue_tile(cur, buf, lane);
     cp_async_commit();
+    if (pub_n) {
+      // the previous batch's publication, deferred to here: its fence waits for that batch's stores to be acknowledged --
+      // with this tile's loads already in flight behind it the warp loses nothing (at the batch's end it cost ~1 us per batch)
+      publish_tiles(p, pend_b, pub_n, lane);
+      pub_n = 0;
+    }
     int t0 = 0, g = 1;
     const bool fetch = !have_next && (u + 1 >= uend);  // on the last tile of the batch: draw the next batch now
     if (fetch) {
@@ -486,14 +499,14 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
     __syncwarp();  // the buffer may be refilled
     if (p.tile_done != nullptr) {
       // one publication per image per drawn batch (a batch is <= batch_max consecutive tiles, mostly of one image)
-      if (cur.b != pend_b) {
+      if (cur.b != pend_b) {  // crossed into another image (rare): the old image's count goes out now
         publish_tiles(p, pend_b, pend_n, lane);
         pend_b = cur.b;
         pend_n = 0;
       }
       ++pend_n;
-      if (u + 1 >= uend) {
-        publish_tiles(p, pend_b, pend_n, lane);
+      if (u + 1 >= uend) {  // batch finished: publish after the next tile's loads have been issued
+        pub_n = pend_n;
         pend_n = 0;
       }
     }
@@ -504,6 +517,12 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
       have_next = true;
     }
     ++u;
+  }
+  if (p.tile_done != nullptr) publish_tiles(p, pend_b, pub_n + pend_n, lane);
+  if (p.trace != nullptr && lane == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMax(p.trace + 9 * p.g.B + 1, t);
   }
   // the last warp to drain re-arms the queue for the next launch
   if (lane == 0) {
@@ -625,6 +644,9 @@ static int launch_decode(const DecodeParams& p, const DecodeShape& sh, cudaStrea
   else if (nsb == 2) fn = (const void*)decode_kernel<2, FORM, PRECISE>;
   else fn = (const void*)decode_kernel<4, FORM, PRECISE>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem_bytes);
+  // Ask for the largest shared-memory carve-out: the SM partition is fixed while a CTA is resident, and the NMS CTA that joins
+  // this one (programmatic dependent, or the previous batch's tail) needs its 82 KB next to our ~109 KB.
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) {
     set_error("decode: cudaFuncSetAttribute(%zu): %s", sh.smem_bytes, cudaGetErrorString(e));
     return FVB_E_CUDA;
@@ -728,6 +750,7 @@ extern "C" int fvb_yolo_decode_sync_f32(const fvb_yolo_geom* geom, const float* 
   p.cand_rec = d_cand_rec;
   p.sched = (unsigned*)d_ws;
   p.tile_done = d_tile_sync;
+  p.trace = debug_trace_ptr();
   FVB_REQUIRE(((uintptr_t)d_tile_sync & 3) == 0, "decode: tile_sync misaligned");
   p.batch_max = knob_batch();
   cudaStream_t s = (cudaStream_t)stream;

@@ -54,9 +54,9 @@ struct YoloNmsParams {
   unsigned tiles_per_image;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -215,22 +215,25 @@ __device__ __forceinline__ void yolo_nms_image(const YoloNmsParams& p, const int
 // barrier -- and then runs the image's NMS while the decode kernel is still streaming the later images.  Only the images
 // decoded last are left when the decode kernel exits, so the step's tail is one image's NMS latency instead of a whole wave's.
 template <bool PDL>
-__global__ void __launch_bounds__(kNmsThreads) yolo_nms_kernel(const YoloNmsParams p) {
+__global__ void __maxnreg__(40) yolo_nms_kernel(const YoloNmsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.x;
   bool ok = true;
+  if (p.trace && threadIdx.x == 0) p.trace[p.B * 8 + b] = gtime_ns();  // CTA entry (before the wait for the image)
   if (PDL) {
     __shared__ int s_ok;
     if (threadIdx.x == 0) {
       const long long t0 = gtime_ns();
       int good = 1;
-      while (ld_acquire_gpu(&p.tile_sync[b]) < p.tiles_per_image) {
-        __nanosleep(256);
+      // relaxed polls (an acquire load per poll would also invalidate this SM's L1 every time), one fence when the count is there
+      while (ld_relaxed_gpu(&p.tile_sync[b]) < p.tiles_per_image) {
+        __nanosleep(512);
         if (gtime_ns() - t0 > 4000000000ll) {  // 4 s: the producer is not running (misuse) -- report instead of hanging the GPU
           good = 0;
           break;
         }
       }
+      __threadfence();      // acquire side of decode_kernel's publish_tiles()
       p.tile_sync[b] = 0u;  // re-armed for the next decode launch (stream-ordered after this grid)
       s_ok = good;
     }
@@ -380,6 +383,7 @@ static int ensure_smem(const void* fn, size_t bytes, const char* what) {
     return FVB_E_LIMIT;
   }
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) {
     set_error("%s: cudaFuncSetAttribute(%zu): %s", what, bytes, cudaGetErrorString(e));
     return FVB_E_CUDA;
@@ -391,11 +395,15 @@ static int ensure_smem(const void* fn, size_t bytes, const char* what) {
 
 using namespace fvb;
 
-// Debug hook (tools/nms_trace.py; declared in the "debug hooks" section of fvb200.h): device buffer [B][8] of globaltimer stamps
-// written by yolo_nms_kernel.  Process-global and NOT thread-safe by design -- the one piece of mutable state outside the
+// Debug hook (tools/nms_trace.py, tools/overlap_probe.py; declared in the "debug hooks" section of fvb200.h): device buffer of
+// 9*B + 2 int64 -- [B][8] globaltimer stamps per phase written by yolo_nms_kernel, [B] CTA entry stamps, then the decode
+// kernel's earliest CTA start / latest CTA end (atomicMin / atomicMax: preset to INT64_MAX / 0).  Process-global and NOT thread-safe by design -- the one piece of mutable state outside the
 // thread-local error string; NULL (the default) disables it and production code never sets it.
 static long long* g_nms_trace = nullptr;
 extern "C" void fvb_debug_set_nms_trace(void* d_buf) { g_nms_trace = (long long*)d_buf; }
+namespace fvb {
+long long* debug_trace_ptr() { return g_nms_trace; }
+}
 
 extern "C" size_t fvb_yolo_nms_workspace_bytes(int batch, int rows_per_image) {
   size_t bn = (size_t)batch * (size_t)rows_per_image;

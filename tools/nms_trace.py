@@ -19,10 +19,11 @@ anc, st = cfg.anchors_levels(), cfg.strides
 ctx = DecodeContext(heads, anc, st)
 res = yolov3_decode(heads, anc, st, ctx=ctx, conf_thres=0.25)
 lib = C.CDLL(_lib.LIB_PATH)
-trace = torch.zeros(B, 8, dtype=torch.int64, device="cuda")
+trace_all = torch.zeros(9 * B + 2, dtype=torch.int64, device="cuda")
+trace = trace_all[:8 * B].view(B, 8)
 for it in range(3):
     non_max_suppression_batched(res, 0.25, 0.45, 300, cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=False)
-lib.fvb_debug_set_nms_trace(C.c_void_p(trace.data_ptr()))
+lib.fvb_debug_set_nms_trace(C.c_void_p(trace_all.data_ptr()))
 non_max_suppression_batched(res, 0.25, 0.45, 300, cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=False)
 torch.cuda.synchronize()
 lib.fvb_debug_set_nms_trace(C.c_void_p(0))
