@@ -175,10 +175,360 @@ def run_reference(args, cfg):
         "config": {"workload": "YOLOv3-416 COCO-shape (80 cls, 3x3 anchors) decode+CIoU loss+NMS, batch 256 per GPU",
                    "step_sample_images": sample, "timed_on": "host CPU"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample_desc},
+                         "sample": sample_desc, "cpu_model": cpu_model_name(), "stages": cpu_stage_baseline()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_stage_baseline(reps=7, warm=2):
+    """the reference's CPU path on config 1 (B=8, 416, C=80), per stage, with all host threads and with
+    one.  When /root/reference is mounted (build container) the stages call the UNMODIFIED reference through oracle/ref_shim.py
+    (kind "reference"); on the GPU box that tree does not exist and the oracle port is timed (kind "port")."""
+    import numpy as np
+    import oracle
+    from oracle import ref_shim
+    cfg, batch = synth.COCO416, 8
+    g = synth.make_generator(1)
+    labels = synth.make_labels(cfg, batch, g)
+    heads = synth.make_heads(cfg, batch, labels, g)
+    anc, st = cfg.anchors_levels(), cfg.strides
+    backend = pick_nms_backend()
+    thr = np.linspace(0.5, 0.95, 10)
+    kind = "port"
+    if ref_shim.available():
+        try:
+            ref = ref_shim.load()
+            kind = "reference"
+        except Exception:
+            ref = None
+    if kind == "reference":
+        class _M:
+            anchors_per_level, backbone_strides_per_level = anc, st
+        loss_fn = ref.Yolov3Loss(_M(), 0.5, 0.05, 1.0, 0.5)
+        decode = lambda: ref.decode(heads, anc, st, cfg.num_classes)                                # noqa: E731
+        loss = lambda: loss_fn(heads, labels)                                                      # noqa: E731
+        nms_one = lambda r: ref.tools.non_max_suppression(r, 0.25, 0.45, 300)                       # noqa: E731
+        new_map = lambda: ref.metrics.CalculateMAP(thr)                                            # noqa: E731
+    else:
+        decode = lambda: oracle.decode.decode(heads, anc, st)                                      # noqa: E731
+        loss = lambda: oracle.loss.yolov3_loss(heads, labels, anc, st)                             # noqa: E731
+        nms_one = lambda r: oracle.nms.nms_lib(r, 0.25, 0.45, 300, backend=backend)                 # noqa: E731
+        new_map = lambda: oracle.map_.MapOracle(thr)                                               # noqa: E731
+    res = decode()
+    dets = [nms_one(res[i]) for i in range(batch)]
+    tgts = [synth.labels_to_pixel_targets(labels, i, cfg.img, cfg.img) for i in range(batch)]
+
+    def nms_loop():
+        for i in range(batch):
+            nms_one(res[i])
+
+    def map_stage():                      # utils/fit.py:96-103: per-image process_one, then fetch
+        est = new_map()
+        for (s_, c_, b_), t in zip(dets, tgts):
+            if s_.numel():
+                est.process_one(torch.cat([c_.float(), s_, b_], 1), t)
+        est.fetch()
+
+    stages = {"decode": decode, "loss": loss, "nms_loop": nms_loop, "map": map_stage}
+    out = {"config": "BASELINE.json configs[0]: YOLOv3-416 COCO-shape, batch 8", "kind": kind, "cpu_model": cpu_model_name(),
+           "nms_backend": "torchvision.ops.nms (CPU)" if (kind == "reference" or backend == "torchvision") else "numpy restatement",
+           "reps": "median of %d after %d warm-ups" % (reps, warm), "threads": {}}
+    prev = torch.get_num_threads()
+    for n in sorted({os.cpu_count() or 1, 1}, reverse=True):
+        torch.set_num_threads(n)
+        row, total = {}, 0.0
+        for name, fn in stages.items():
+            for _ in range(warm):
+                fn()
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            med = statistics.median(ts)
+            total += med
+            row[name] = {"ms": med * 1e3, "images_per_s": batch / med}
+        row["total"] = {"ms": total * 1e3, "images_per_s": batch / total}
+        out["threads"][str(n)] = row
+    torch.set_num_threads(prev)
+    return out
+
+
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs nearest to GPU `index` BEFORE any pinned host buffer is allocated (first-touch places the pages
+    on that NUMA node), so that N ranks do not all stream their H2D copies out of node 0.  Returns the affinity size or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
+def decode_source_sha():
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("decode.cu", "common.cuh"):
+        with open(os.path.join(ROOT, "fastvision_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per decode launch from the tracked ncu capture -- only if that capture was
+    taken from THIS decode kernel source (profiles/decode_traffic.json is keyed by the source hash; tools/update_traffic.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "decode_traffic.json")) as f:
+            rec = json.load(f)
+        if rec.get("source_sha16") == decode_source_sha():
+            return rec.get("dram_bytes_per_launch"), rec.get("capture")
+        return None, "stale: profiles/decode_traffic.json was captured from another decode.cu (%s)" % rec.get("source_sha16")
+    except Exception:
+        return None, "no capture"
+
+
+def time_step_loop(step, dh, dl, k, dev, barrier, in_graph, distributed):
+    """ms per step of k back-to-back steps (device events); one CUDA graph when `in_graph`, eager launches otherwise."""
+    for _ in range(3):
+        step(dh, dl)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g = None
+    if in_graph:
+        g = torch.cuda.CUDAGraph()
+        cs = torch.cuda.Stream(device=dev)
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(g, stream=cs):
+            for _ in range(k):
+                step._head(dh, dl)
+                step._decode(dh)
+                step._tail(dh, dl, reduce_inside=distributed)
+        torch.cuda.current_stream().wait_stream(cs)
+        g.replay()
+        torch.cuda.synchronize()
+    barrier()
+    t0.record()
+    if g is not None:
+        g.replay()
+    else:
+        for _ in range(k):
+            step(dh, dl)
+    t1.record()
+    barrier()
+    return t0.elapsed_time(t1) / k
+
+
+def strong_config3(rank, world, dev, dist, barrier, k=50):
+    """BASELINE.json configs[2]: ONE global batch of 1024 YOLOv3-608 / 10-class images, first on rank 0 alone, then sharded
+    1024/N per rank (the reference's only parallel mode is a scatter of the batch: nn.DataParallel,
+    demos/yolov3_huaweiShip/train.py:104).  The 1024 images are 1024/128 copies of one seeded 128-image block (generation on
+    the CPU is what bounds the bench's run time); every copy is a distinct tensor region, so nothing is served from cache."""
+    from fastvision_b200.pipeline import ValStep
+    cfg, total = synth.SHIP608, 1024
+    if total % world:
+        return {"skipped": "1024 images do not divide over %d ranks" % world}
+    per = total // world
+    block = 128 if per % 128 == 0 else per
+    g = synth.make_generator(3)
+    lab_b = synth.make_labels(cfg, block, g)
+    hb = [h.to(dev) for h in synth.make_heads(cfg, block, lab_b, g)]
+
+    def tiled(copies):
+        heads = [h.repeat(copies, 1, 1, 1, 1).contiguous() for h in hb]
+        labs = []
+        for c in range(copies):
+            t = lab_b.clone()
+            t[:, 0] += c * block
+            labs.append(t)
+        return heads, torch.cat(labs).to(dev)
+
+    res = {"workload": "YOLOv3-608, 10 classes, global batch 1024 (BASELINE.json configs[2])", "steps": k}
+    full_loss = full_cnt = None
+    if rank == 0:
+        fh, fl_ = tiled(total // block)
+        full = ValStep(cfg.anchors_levels(), cfg.strides, data_parallel=False)
+        res["ms_full_1gpu"] = time_step_loop(full, fh, fl_, k, dev, lambda: torch.cuda.synchronize(), True, False)
+        full_loss = float(full.out["loss"])
+        full_cnt = full.out["cnt"][:per].clone()
+        full_boxes = full.out["boxes"][:per].clone()
+        del full, fh, fl_
+        torch.cuda.empty_cache()
+    barrier()
+    sh, sl = tiled(per // block)
+    step = ValStep(cfg.anchors_levels(), cfg.strides, batch_global=total)
+    step(sh, sl)
+    in_graph = step._peer() is not None
+    ms = time_step_loop(step, sh, sl, k, dev, barrier, in_graph, True)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["ms_sharded"] = float(t.item())
+    res["images_per_rank"] = per
+    res["launch"] = "one CUDA graph of %d steps (peer-memory reduce inside)" % k if in_graph else "eager launches (NCCL all-reduce)"
+    if rank == 0:
+        res["speedup"] = res["ms_full_1gpu"] / res["ms_sharded"]
+        res["images_per_s"] = total / (res["ms_sharded"] * 1e-3)
+        rel = abs(float(step.out["loss"]) - full_loss) / abs(full_loss)
+        same = bool(torch.equal(step.out["cnt"], full_cnt))
+        for i in range(per):
+            c = int(full_cnt[i])
+            same = same and bool(torch.equal(step.out["boxes"][i, :c], full_boxes[i, :c]))
+        res["parity"] = {"loss_rel_diff_sharded_vs_full": rel, "detections_bit_equal": same}
+        if rel > 1e-6 or not same:
+            raise SystemExit("bench.py: config-3 sharded step differs from the full-batch step: %s" % res["parity"])
+    del step, sh, sl
+    torch.cuda.empty_cache()
+    return res
+
+
+def dp_parity(step, dh, dl, batch, rank, world, dev, dist, cfg):
+    """Outside the timed region: the sharded step against ONE single-GPU step over the gathered global batch (rank 0).
+    loss/yolov3_loss.py:52,58,64 normalise by GLOBAL counts, so the sharded loss must equal the full-batch loss (rtol 1e-6) and
+    every image's detections must be bit-equal.  Any difference fails the run."""
+    from fastvision_b200.pipeline import ValStep
+    out = step(dh, dl)
+    torch.cuda.synchronize()
+    gh = []
+    for h in dh:
+        buf = torch.empty((world * h.size(0),) + tuple(h.shape[1:]), dtype=h.dtype, device=dev)
+        dist.all_gather_into_tensor(buf, h.contiguous())
+        gh.append(buf)
+    nlab = torch.tensor([dl.size(0)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(nlab) for _ in range(world)]
+    dist.all_gather(counts, nlab)
+    counts = [int(c.item()) for c in counts]
+    pad = torch.zeros(max(counts), 6, dtype=dl.dtype, device=dev)
+    pad[:dl.size(0)] = dl
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    labs = []
+    for r, (p_, c) in enumerate(zip(parts, counts)):
+        t = p_[:c].clone()
+        t[:, 0] += r * batch
+        labs.append(t)
+    keys = ("cnt", "boxes", "scores", "cls")
+    gathered = {}
+    for key in keys:
+        t = out[key].contiguous()
+        buf = torch.empty((world * t.size(0),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        dist.all_gather_into_tensor(buf, t)
+        gathered[key] = buf
+    res = None
+    if rank == 0:
+        full = ValStep(cfg.anchors_levels(), cfg.strides, data_parallel=False)
+        fo = full(gh, torch.cat(labs))
+        torch.cuda.synchronize()
+        rel = abs(float(out["loss"]) - float(fo["loss"])) / abs(float(fo["loss"]))
+        ok = bool(torch.equal(gathered["cnt"], fo["cnt"]))
+        valid = torch.arange(fo["boxes"].size(1), device=dev)[None, :] < fo["cnt"][:, None]
+        for key in ("boxes", "scores", "cls"):
+            ok = ok and bool(torch.equal(gathered[key][valid], fo[key][valid]))
+        res = {"status": "ok" if (ok and rel <= 1e-6) else "FAILED", "loss_rel_diff": rel, "detections_bit_equal": ok,
+               "images_compared": world * batch,
+               "how": "all ranks' heads/labels all-gathered to rank 0, one single-GPU step over the %d-image global batch" % (world * batch)}
+        del full
+    del gh, gathered
+    torch.cuda.empty_cache()
+    flag = torch.tensor([1 if (res is None or res["status"] == "ok") else 0], device=dev)
+    dist.broadcast(flag, 0)
+    if int(flag.item()) != 1:
+        raise SystemExit("bench.py: dp_parity FAILED: %s" % (res,))
+    return res
+
+
+def config5_map(step, labels, cfg, batch, rank, world, dev, distributed, barrier):
+    """BASELINE.json configs[4]: mAP@[.5:.95] over 5000 synthetic images, 5000/N per rank: per-rank matcher (one launch), the
+    evidence gathered over NCCL (dist.gather_map_state), AP integration once on rank 0 -- utils/fit.py:94-103,
+    metrics/map.py:120-141.  Detections are this rank's NMS output of the timed batch, image j re-using batch image j mod B with
+    a seeded per-image box jitter; checked against a single-GPU evaluation of the gathered raw detections."""
+    import numpy as np
+    from fastvision_b200.metrics import CalculateMAP
+    from fastvision_b200 import dist as fdist
+    total = 5000
+    lo, hi = fdist.shard_range(total, rank, world)
+    n_img = hi - lo
+    out = step.out
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20220504 + 5000)
+    jitter_all = (torch.rand(total, 1, 4, generator=gen, device=dev) - 0.5) * 4.0       # +-2 px, keyed by GLOBAL image id
+    src = torch.arange(lo, hi, device=dev) % batch
+    cnt = out["cnt"][src].long()
+    md = out["boxes"].size(1)
+    valid = torch.arange(md, device=dev)[None, :] < cnt[:, None]
+    boxes = out["boxes"][src] + jitter_all[lo:hi]
+    dets = torch.cat([out["cls"][src].float().unsqueeze(-1), out["scores"][src].unsqueeze(-1), boxes], 2)[valid].contiguous()
+    det_off = torch.zeros(n_img + 1, dtype=torch.int32, device=dev)
+    det_off[1:] = torch.cumsum(cnt, 0)
+    lab = labels.to(dev)
+    per_img = torch.bincount(lab[:, 0].long(), minlength=batch)
+    starts = torch.cumsum(per_img, 0) - per_img
+    half = lab[:, 4:6] / 2
+    gt_all = torch.cat([lab[:, 1:2], (lab[:, 2:4] - half) * cfg.img, (lab[:, 2:4] + half) * cfg.img], 1)
+    g_cnt = per_img[src]
+    gt_off = torch.zeros(n_img + 1, dtype=torch.int32, device=dev)
+    gt_off[1:] = torch.cumsum(g_cnt, 0)
+    idx = torch.repeat_interleave(starts[src], g_cnt) + (torch.arange(int(g_cnt.sum()), device=dev) - torch.repeat_interleave(gt_off[:-1].long(), g_cnt))
+    gts = gt_all[idx].contiguous()
+    thr = np.linspace(0.5, 0.95, 10)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    est = CalculateMAP(thr)
+    est.process_batch(dets, det_off, gts, gt_off)                # warm-up (workspace)
+    est = CalculateMAP(thr)
+    barrier()
+    ev[0].record()
+    est.process_batch(dets, det_off, gts, gt_off)
+    ev[1].record()
+    rows, tcls = est.state()
+    if distributed:
+        rows, tcls = fdist.gather_map_state(rows, tcls)
+    ev[2].record()
+    result = None
+    if rank == 0:
+        est.load_state(rows, tcls)
+        result = est.fetch()
+    ev[3].record()
+    torch.cuda.synchronize()
+    times = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])], dtype=torch.float64, device=dev)
+    if distributed:
+        import torch.distributed as dist
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        all_dets = fdist.all_gather_rows(torch.cat([dets, torch.repeat_interleave(torch.arange(lo, hi, device=dev), cnt).float()[:, None]], 1))
+        all_gts = fdist.all_gather_rows(torch.cat([gts, torch.repeat_interleave(torch.arange(lo, hi, device=dev), g_cnt).float()[:, None]], 1))
+    else:
+        all_dets = all_gts = None
+    res = None
+    if rank == 0:
+        parity = "n/a (one rank)"
+        if distributed:
+            d_img, g_img = all_dets[:, 6].long(), all_gts[:, 5].long()
+            doff = torch.zeros(total + 1, dtype=torch.int32, device=dev)
+            doff[1:] = torch.cumsum(torch.bincount(d_img, minlength=total), 0)
+            goff = torch.zeros(total + 1, dtype=torch.int32, device=dev)
+            goff[1:] = torch.cumsum(torch.bincount(g_img, minlength=total), 0)
+            one = CalculateMAP(thr)
+            one.process_batch(all_dets[:, :6].contiguous(), doff, all_gts[:, :5].contiguous(), goff)
+            want = one.fetch()
+            same = bool(np.array_equal(want[0], result[0])) and bool(np.array_equal(want[1], result[1])) and want[2] == result[2]
+            parity = "ok" if same else "FAILED"
+            if not same:
+                raise SystemExit("bench.py: config-5 gathered mAP differs from the single-GPU mAP")
+        res = {"images": total, "images_per_rank": n_img, "detections": int(rows.size(0)), "match_ms": float(times[0]),
+               "gather_ms": float(times[1]), "fetch_ms": float(times[2]), "images_per_s": total / (float(times.sum()) * 1e-3),
+               "map50": float(result[0][0]), "map": float(result[0].mean()), "classes": len(result[2]),
+               "parity_vs_single_gpu": parity}
+    return res
 
 
 # ------------------------------------------------------------------------------------------ CUDA leg
@@ -190,6 +540,7 @@ def run_cuda(args, cfg):
     from fastvision_b200.pipeline import ValStep
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local)      # before the pinned host buffers exist
     distributed = world > 1
     if distributed:
         import torch.distributed as dist
@@ -377,7 +728,20 @@ def run_cuda(args, cfg):
     if distributed:
         dist.all_reduce(tp2, op=dist.ReduceOp.MAX)
     e2e_value = batch * world * ke / float(tp2.item())
+    e2e_seconds = float(tp2.item())
     del dh2, dl2, step2, sets
+    # the host-side ceiling of that loop: the same pinned -> device copies with NO kernels, all ranks at once
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        for dst, src in zip(dh, host_heads):
+            dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    h2d_copy_only_gbps = h2d * ke / float(tc.item()) / 1e9
 
     # ---- extra (reported in config, not the headline): the cross-batch pipeline, tail of batch i under decode i+1 ----
     from fastvision_b200.pipeline import ValPipeline
@@ -400,6 +764,13 @@ def run_cuda(args, cfg):
     pipelined_ms = float(tp.item()) / kp
     del pipe
 
+    # ---- correctness and the other BASELINE configs, outside the timed region ---------------------------------------------
+    extras = {}
+    if not args.no_extras:
+        extras["config5_map"] = config5_map(step, labels, cfg, batch, rank, world, dev, distributed, barrier)
+        if distributed:
+            extras["dp_parity"] = dp_parity(step, dh, dl, batch, rank, world, dev, dist, cfg)
+            extras["strong_config3"] = strong_config3(rank, world, dev, dist, barrier)
     if unrolled is not None:
         step_launch = ("the K steps captured back to back in one CUDA graph (decode -> NMS branch || loss branch%s), every decode "
                        "kernel between its own pair of external timing-event nodes" %
@@ -418,14 +789,7 @@ def run_cuda(args, cfg):
         alg_bytes = 2 * batch * rows * step.ctx.k * 4          # one read of the heads + one write of results
         dec_avg = sum(decode_ms) / len(decode_ms)
         achieved = alg_bytes / (dec_avg * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "decode_traffic_bytes.json")
-        if os.path.exists(tpath):
-            try:
-                with open(tpath) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        traffic, traffic_src = measured_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms_max / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -443,12 +807,15 @@ def run_cuda(args, cfg):
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": ke, "serial_value": e2e_serial,
+                    "h2d_gbps_per_rank": h2d * ke / e2e_seconds / 1e9, "h2d_copy_only_gbps_per_rank": h2d_copy_only_gbps,
+                    "cpu_affinity_cpus": affinity,
                     "note": "pinned host heads+labels copied H2D, ValStep public call, loss + padded detections copied D2H and read by the "
                             "host, every step; double-buffered (the copy of step i+1 overlaps the kernels of step i); serial_value = "
                             "the same loop with no overlap"},
             "gpu_launches": launches_per_step * k,
             "roofline": {"bound": "hbm", "kernel": "fvb::decode_kernel (decode + candidate bitmap/records + objectness-BCE partials)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dec_avg,
                          "launches_timed": "%d of the %d decode launches of the timed region (every %d-th), CUDA events" % (len(sampled), k, every), "peak_source": peak_src,
                          "step_achieved": alg_bytes * world / (total_ms_max / k * 1e-3) / 1e9 / world,
@@ -456,13 +823,19 @@ def run_cuda(args, cfg):
         }
         if per_rank is not None:
             line["config"]["per_rank"] = per_rank
+        for key, val in extras.items():
+            if val is not None:
+                line["config"][key] = val
+        if "dp_parity" in extras and extras["dp_parity"] is not None:
+            line["dp_parity"] = extras["dp_parity"]["status"]
         if not args.no_cpu_baseline and world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             v, med, reps, backend = time_cpu_reference(cfg, args.cpu_sample, 0, args.cpu_budget, 3, 1)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                 "sample": "%d-image slice of the same workload (same generator/seed), %d passes, median %.3f s/pass; oracle port "
-                          "(torch-CPU restatement of the reference, NMS backend '%s')" % (args.cpu_sample, reps, med, backend)}
+                          "(torch-CPU restatement of the reference, NMS backend '%s')" % (args.cpu_sample, reps, med, backend),
+                "cpu_model": cpu_model_name(), "stages": cpu_stage_baseline()}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
@@ -484,6 +857,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-event-every", type=int, default=8, help="bracket every n-th decode launch with timing events")
     ap.add_argument("--no-unrolled-graph", action="store_true", help="time per-step launches instead of one K-step CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="skip config-5 mAP, dp_parity and config-3 strong scaling")
     args = ap.parse_args()
     cfg = synth.COCO416
     if args.impl == "reference":

@@ -43,6 +43,7 @@ _SIGS = {
     "fvb_yolo_decode_workspace_bytes": (C.c_size_t, []),
     "fvb_yolo_decode_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), C.c_int, C.c_int, _P, C.c_float, _P, _P, _P, _P, _P]),
     "fvb_yolo_decode_tiles_per_image": (C.c_int, [C.POINTER(Geom)]),
+    "fvb_yolo_decode_leaves_room_for_nms": (C.c_int, [C.POINTER(Geom)]),
     "fvb_yolo_decode_sync_f32": (C.c_int, [C.POINTER(Geom), C.POINTER(_P), C.c_int, C.c_int, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
     "fvb_box_convert_f32": (C.c_int, [_P, C.c_int64, C.c_int, C.c_float, C.c_float, _P, _P]),
     "fvb_iou_elementwise_f32": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
@@ -97,6 +98,7 @@ _SIGS = {
     "fvb_map_ap_f64": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fvb_kmeans_workspace_bytes": (C.c_size_t, [C.c_int]),
     "fvb_kmeans_step_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
+    "fvb_val_evidence_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_int64, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     "fvb_debug_set_nms_trace": (None, [_P]),
     "fvb_debug_reload_knobs": (None, []),
 }

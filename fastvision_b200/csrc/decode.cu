@@ -700,6 +700,19 @@ extern "C" int fvb_yolo_decode_tiles_per_image(const fvb_yolo_geom* geom) {
   return t;
 }
 
+// Can one NMS CTA (512 threads x 40 registers, nms.cu) be resident beside a decode CTA of this geometry?  Only then does the
+// programmatic-dependent NMS really run under the decode; otherwise its CTAs just queue until decode CTAs leave.
+extern "C" int fvb_yolo_decode_leaves_room_for_nms(const fvb_yolo_geom* geom) {
+  Geom g;
+  if (make_geom(geom, nullptr, &g) != FVB_OK) return -1;
+  if (g.B == 0) return 0;
+  DecodeShape sh;
+  if (decode_launch_shape(g, &sh) != FVB_OK) return -1;
+  const int regs = sh.warps_per_cta * 32 * 64 + 512 * 40;
+  const size_t smem = sh.smem_bytes + 84 * 1024 + 2 * 1024;
+  return (regs <= 65536 && smem <= 228 * 1024 && sh.warps_per_cta * 32 + 512 <= 2048) ? 1 : 0;
+}
+
 extern "C" int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
                                    float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
                                    double* d_conf_bce0, void* d_ws, void* stream) {

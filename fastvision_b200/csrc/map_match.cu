@@ -22,23 +22,49 @@ struct MapParams {
   int* ws_best;  // [sum M] scratch: best target of each detection (global, sized like dets)
 };
 
+constexpr int kMapGtCap = 1024;  // targets of one image staged in shared memory (20 KB); beyond: the global-memory path
+
+// One CTA per image.  The image's targets are staged in shared memory once (every detection walks all of them); the dedupe
+// "lowest-index p with t*(p) = t wins" is an atomicMin per target instead of a serial scan over the earlier detections.
 __global__ void __launch_bounds__(kMapThreads) map_match_kernel(const MapParams p, float* ws_iou) {
+  __shared__ float4 s_box[kMapGtCap];
+  __shared__ float s_cls[kMapGtCap];
+  __shared__ int s_win[kMapGtCap];
   const int img = blockIdx.x;
   const int d0 = p.det_off[img], M = p.det_off[img + 1] - d0;
   const int g0 = p.gt_off[img], N = p.gt_off[img + 1] - g0;
   if (M <= 0) return;
   const float thr0 = (float)p.thr[0];  // torch compares the fp32 IoU tensor with the scalar folded to fp32 (map.py:51)
+  const bool staged = N <= kMapGtCap;
+  if (staged) {
+    for (int t = threadIdx.x; t < N; t += kMapThreads) {
+      const float* g = p.gts + (size_t)(g0 + t) * 5;
+      s_cls[t] = g[0];
+      s_box[t] = make_float4(g[1], g[2], g[3], g[4]);
+      s_win[t] = 0x7fffffff;
+    }
+    __syncthreads();
+  }
   for (int q = threadIdx.x; q < M; q += kMapThreads) {
     const float* d = p.dets + (size_t)(d0 + q) * 6;
+    const float dcls = d[0];
     Box pb;
     pb.x1 = d[2]; pb.y1 = d[3]; pb.x2 = d[4]; pb.y2 = d[5];
     float best = -1.0f;
     int bt = -1;
     for (int t = 0; t < N; ++t) {
-      const float* g = p.gts + (size_t)(g0 + t) * 5;
-      if (g[0] != d[0]) continue;  // map.py:54 class equality on floats
+      float gc;
       Box tb;
-      tb.x1 = g[1]; tb.y1 = g[2]; tb.x2 = g[3]; tb.y2 = g[4];
+      if (staged) {
+        gc = s_cls[t];
+        const float4 b4 = s_box[t];
+        tb.x1 = b4.x; tb.y1 = b4.y; tb.x2 = b4.z; tb.y2 = b4.w;
+      } else {
+        const float* g = p.gts + (size_t)(g0 + t) * 5;
+        gc = g[0];
+        tb.x1 = g[1]; tb.y1 = g[2]; tb.x2 = g[3]; tb.y2 = g[4];
+      }
+      if (gc != dcls) continue;  // map.py:54 class equality on floats
       float iou = iou_plain<false>(tb, pb, 1e-7f);  // cal_iou_batch(target, predict), map.py:50
       if (iou > thr0 && iou > best) {
         best = iou;
@@ -47,14 +73,19 @@ __global__ void __launch_bounds__(kMapThreads) map_match_kernel(const MapParams 
     }
     p.ws_best[d0 + q] = bt;
     ws_iou[d0 + q] = best;
+    if (staged && bt >= 0) atomicMin(&s_win[bt], q);
   }
   __syncthreads();
   for (int q = threadIdx.x; q < M; q += kMapThreads) {
-    int bt = p.ws_best[d0 + q];
+    const int bt = p.ws_best[d0 + q];
     bool win = bt >= 0;
-    for (int q2 = 0; win && q2 < q; ++q2)
-      if (p.ws_best[d0 + q2] == bt) win = false;
-    double iou = (double)ws_iou[d0 + q];
+    if (staged) {
+      win = win && s_win[bt] == q;
+    } else {
+      for (int q2 = 0; win && q2 < q; ++q2)
+        if (p.ws_best[d0 + q2] == bt) win = false;
+    }
+    const double iou = (double)ws_iou[d0 + q];
     unsigned char* c = p.correct + (size_t)(d0 + q) * p.n_thr;
     for (int k = 0; k < p.n_thr; ++k) c[k] = (win && iou > p.thr[k]) ? 1 : 0;  // map.py:81 (numpy: fp32 vs f64)
   }

@@ -153,6 +153,9 @@ class Yolov3(nn.Module):
         self.head = head(feature_channels=self.backbone_channels_per_level, num_levels=len(self.backbone_channels_per_level),
                          num_anchors_per_level=num_anchors_per_level, num_classes=num_classes)
         self._ctx = None
+        # False: forward returns (head_out, None) in eval mode -- for callers that decode the raw heads themselves
+        # (fastvision_b200.utils.Fit._val runs the fused decode + NMS + loss step and would otherwise decode twice)
+        self.decode_in_forward = True
 
     def decode(self, head_out):
         ctx = self._ctx
@@ -167,7 +170,7 @@ class Yolov3(nn.Module):
     def forward(self, images, val=False):
         head_out = self.head(self.neck(self.backbone(images)))
         if self.training == False or val == True:            # noqa: E712  (yolov3.py:34)
-            return (head_out, self.decode(head_out))
+            return (head_out, self.decode(head_out) if self.decode_in_forward else None)
         return head_out
 
 

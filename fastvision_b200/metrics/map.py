@@ -19,9 +19,51 @@ class CalculateMAP:
         self.map_iou_values = np.asarray(map_iou_values, dtype=np.float64)
         if self.map_iou_values.size > 16:
             raise ValueError("at most 16 IoU thresholds")
-        self._dets = []          # device [M,6] blocks = [cls, conf, x1,y1,x2,y2]
-        self._correct = []       # device u8 [M, n_thr] blocks
-        self._targets = []       # device f32 target classes
+        self._dets_list = []     # device [M,6] blocks = [cls, conf, x1,y1,x2,y2]
+        self._correct_list = []  # device u8 [M, n_thr] blocks
+        self._targets_list = []  # device f32 target classes
+        self._pending = []       # capacity-shaped batches of process_padded: (dets, correct, det_off, gts, gt_off)
+
+    # Batches recorded by ``process_padded`` keep capacity shapes (no host sync while the loader runs); their valid row counts
+    # are read in ONE transfer the first time the evidence is needed (``fetch`` / ``state`` / the reference's accumulators).
+    def _flush(self):
+        if not self._pending:
+            return
+        totals = torch.stack([torch.stack([d_off[-1], g_off[-1]]) for _, _, d_off, _, g_off in self._pending]).cpu().tolist()
+        for (dets, correct, _, gts, _), (nd, ng) in zip(self._pending, totals):
+            if ng:
+                self._targets_list.append(gts[:ng, 0].contiguous())
+            if nd:
+                self._dets_list.append(dets[:nd])
+                self._correct_list.append(correct[:nd])
+        self._pending = []
+
+    @property
+    def _dets(self):
+        self._flush()
+        return self._dets_list
+
+    @_dets.setter
+    def _dets(self, v):
+        self._pending, self._dets_list = [], v
+
+    @property
+    def _correct(self):
+        self._flush()
+        return self._correct_list
+
+    @_correct.setter
+    def _correct(self, v):
+        self._correct_list = v
+
+    @property
+    def _targets(self):
+        self._flush()
+        return self._targets_list
+
+    @_targets.setter
+    def _targets(self, v):
+        self._targets_list = v
 
     # the reference's public accumulators (map.py:13-14), materialised on the host on demand
     @property
@@ -70,6 +112,30 @@ class CalculateMAP:
             return
         self._dets.append(dets.detach())
         self._correct.append(correct)
+
+    def process_padded(self, boxes, scores, cls, cnt, labels, img_w, img_h):
+        """The whole per-image loop of utils/fit.py:94-101 for one batch, on the device and WITHOUT a host sync: the padded NMS
+        outputs (boxes [B,max_det,4] xyxy, scores, cls int64, cnt int32) and the batch's labels [T,6] become compact detection
+        rows + pixel-unit targets (``fvb_val_evidence_f32``), then one matcher launch.  Row counts stay on the device until
+        ``fetch``."""
+        boxes = _lib.require_cuda(boxes, "boxes")
+        scores = _lib.require_cuda(scores, "scores")
+        cls = _lib.require_cuda(cls, "cls", torch.int64)
+        cnt = _lib.require_cuda(cnt, "cnt", torch.int32)
+        labels = _lib.require_cuda(labels, "labels").view(-1, 6)
+        b, md = boxes.size(0), boxes.size(1)
+        t, dev = labels.size(0), boxes.device
+        dets = torch.empty(b * md, 6, dtype=torch.float32, device=dev)
+        gts = torch.empty(max(t, 1), 5, dtype=torch.float32, device=dev)
+        det_off = torch.empty(b + 1, dtype=torch.int32, device=dev)
+        gt_off = torch.empty(b + 1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().fvb_val_evidence_f32(_lib.dptr(boxes), _lib.dptr(scores), _lib.dptr(cls), _lib.dptr(cnt), b, md,
+                                                        _lib.dptr(labels), t, float(img_w), float(img_h), _lib.dptr(dets),
+                                                        _lib.dptr(det_off), _lib.dptr(gts), _lib.dptr(gt_off), _lib.stream()),
+                       "val_evidence")
+        correct = self.match(dets, det_off, gts, gt_off)
+        self._pending.append((dets, correct, det_off, gts, gt_off))
 
     def process_one(self, y_pred, y_true):
         """metrics/map.py:16-83.  y_pred[M,6]=[cls,conf,x1,y1,x2,y2]; y_true[N,5]=[cls,x1,y1,x2,y2]."""

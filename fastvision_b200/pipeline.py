@@ -30,7 +30,8 @@ class _ModelStub:
 class ValStep:
     def __init__(self, anchors_per_level, strides, conf_thres=0.25, iou_thres=0.45, max_det=300,
                  ratio_box=0.05, ratio_conf=1.0, ratio_cls=0.5, nms_flavour="lib", precise_decode=False,
-                 process_group=None, batch_global: Optional[int] = None, overlap_nms=True):
+                 process_group=None, batch_global: Optional[int] = None, overlap_nms: Optional[bool] = None,
+                 data_parallel: Optional[bool] = None):
         self.anchors_per_level = anchors_per_level
         self.strides = strides
         self.conf_thres, self.iou_thres, self.max_det = conf_thres, iou_thres, max_det
@@ -39,6 +40,7 @@ class ValStep:
         self.loss_fn = Yolov3Loss(_ModelStub(anchors_per_level, strides), 0.5, ratio_box, ratio_conf, ratio_cls)
         self.pg = process_group
         self.batch_global = batch_global
+        self.data_parallel = data_parallel     # None: follow torch.distributed; False: a local step even inside a process group
         self.ctx = None
         self.graph = None
         self.out = None
@@ -48,7 +50,9 @@ class ValStep:
         self._peer_reducer = False       # not looked up yet
         # image b's NMS starts as soon as image b is decoded: the NMS kernel is launched as a programmatic dependent of the
         # decode kernel and follows its per-image progress counters (fvb_yolo_decode_sync_f32 / fvb_yolo_nms_after_decode_f32)
-        self.overlap_nms = overlap_nms
+        # (None: decided per head geometry in _prepare -- on when an NMS CTA fits on an SM beside a decode CTA)
+        self._overlap_request = overlap_nms
+        self.overlap_nms = bool(overlap_nms)
         self._ws = _lib.Workspaces()     # owned by this step: a captured graph has these pointers baked in
 
     def _prepare(self, heads):
@@ -71,6 +75,8 @@ class ValStep:
         ctx.records()
         ctx.bce0()
         ctx.tile_sync()
+        if self._overlap_request is None:
+            self.overlap_nms = _lib.load().fvb_yolo_decode_leaves_room_for_nms(ctx.geom) == 1
         self._nms_ws = self._ws.get("yolo_nms", _lib.load().fvb_yolo_nms_workspace_bytes(b, ctx.rows), dev)
         self.graph = None
         # NMS (latency-bound, one CTA per image) and the loss kernels only depend on the decode: they run as
@@ -81,6 +87,8 @@ class ValStep:
         self._ev_start = torch.cuda.Event()
 
     def _distributed(self):
+        if self.data_parallel is not None:
+            return bool(self.data_parallel)
         return self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                        and torch.distributed.get_world_size() > 1)
 

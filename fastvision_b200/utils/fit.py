@@ -83,30 +83,26 @@ class Fit():
         step = self._val_step
         loss_value = None
         self.model.eval()
-        with torch.no_grad():
-            for batch in self.train_loader:                                # (sic: the reference validates on train_loader, :80)
-                images, labels = self._to_device(*batch)
-                head_out = self.model(images)                              # raw heads; the fused step decodes them itself
-                out = step(head_out, labels)
-                loss_value = out["loss"]
-                # detections of the whole batch as [sum k, 6] = [cls, conf, x1, y1, x2, y2] + CSR offsets (utils/fit.py:94-96)
-                cnt = out["cnt"].long()
-                b, md = cnt.numel(), out["boxes"].size(1)
-                det_off = torch.zeros(b + 1, dtype=torch.int32, device=cnt.device)
-                det_off[1:] = torch.cumsum(cnt, 0)
-                valid = torch.arange(md, device=cnt.device)[None, :] < cnt[:, None]
-                dets = torch.cat([out["cls"].float().unsqueeze(-1), out["scores"].unsqueeze(-1), out["boxes"]], 2)[valid]
-                # targets: xywh (normalised) -> xyxy pixels, grouped by image (:98-99)
-                whwh = torch.tensor([images.size(3), images.size(2), images.size(3), images.size(2)], dtype=labels.dtype,
-                                    device=labels.device)
-                order = torch.argsort(labels[:, 0], stable=True)
-                lab = labels[order]
-                half = lab[:, 4:6] / 2
-                gts = torch.cat([lab[:, 1:2], (lab[:, 2:4] - half), (lab[:, 2:4] + half)], 1)
-                gts[:, 1:] = gts[:, 1:] * whwh
-                gt_off = torch.zeros(b + 1, dtype=torch.int32, device=cnt.device)
-                gt_off[1:] = torch.cumsum(torch.bincount(lab[:, 0].long(), minlength=b)[:b], 0)
-                map_est.process_batch(dets.contiguous(), det_off, gts.contiguous(), gt_off)
+        # In eval mode the reference's Yolov3.forward returns (head_out, results) (detection/models/yolov3.py:33-54); the fused
+        # step decodes the raw heads itself, so the drop-in model is told to skip its own decode (a reference model that cannot
+        # be told simply has its `results` ignored).
+        had = getattr(core, "decode_in_forward", None)
+        if had is not None:
+            core.decode_in_forward = False
+        try:
+            with torch.no_grad():
+                for batch in self.train_loader:                            # (sic: the reference validates on train_loader, :80)
+                    images, labels = self._to_device(*batch)
+                    model_out = self.model(images)
+                    head_out = model_out[0] if isinstance(model_out, tuple) else model_out
+                    out = step(head_out, labels)
+                    loss_value = out["loss"]
+                    # utils/fit.py:94-101 for the whole batch: detections [cls, conf, xyxy] + pixel-unit targets + the matcher,
+                    # three launches, no host sync (row counts stay on the device until fetch)
+                    map_est.process_padded(out["boxes"], out["scores"], out["cls"], out["cnt"], labels, images.size(3), images.size(2))
+        finally:
+            if had is not None:
+                core.decode_in_forward = had
         map_each_iou, map_each_cls, map_each_cls_idx = map_est.fetch()
         loss_value = float(loss_value) if loss_value is not None else float('nan')
         self.val_result = (loss_value, map_each_iou, map_each_cls, map_each_cls_idx)

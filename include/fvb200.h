@@ -118,6 +118,9 @@ int fvb_yolo_decode_f32(const fvb_yolo_geom* geom, const float* const* d_heads, 
  * bits, records and objectness partials are visible once it reads fvb_yolo_decode_tiles_per_image(geom)); the consumer,
  * fvb_yolo_nms_after_decode_f32, must be the NEXT launch on `stream` and leaves the array zero again.  NULL = plain decode. */
 int fvb_yolo_decode_tiles_per_image(const fvb_yolo_geom* geom);
+/* 1 if an NMS CTA fits on an SM beside a decode CTA of this geometry (registers / shared memory), i.e. if the pair below really
+ * overlaps; 0 if not (narrow rows run 24 decode warps: the pair is then correct but no faster than the plain calls); < 0 on error. */
+int fvb_yolo_decode_leaves_room_for_nms(const fvb_yolo_geom* geom);
 int fvb_yolo_decode_sync_f32(const fvb_yolo_geom* geom, const float* const* d_heads, int form, int precise,
                              float* d_results, float conf_thr, uint32_t* d_cand_bitmap, float* d_cand_rec,
                              double* d_conf_bce0, uint32_t* d_tile_sync, void* d_ws, void* stream);
@@ -353,6 +356,18 @@ int fvb_map_ap_f64(const float* d_dets, const uint8_t* d_correct, int64_t n_dets
 size_t fvb_kmeans_workspace_bytes(int k);
 int fvb_kmeans_step_f32(const float* d_samples, int64_t n, const float* d_centers, int k, float eps, int64_t* d_categories,
                         float* d_new_centers, void* d_ws, void* stream);
+
+/* ---- validation-loop glue ---------------------------------------------------------------------
+ * fvb_val_evidence_f32: what utils/fit.py:94-99 builds per image in Python, for a whole batch without a host sync:
+ * the padded outputs of fvb_yolo_nms_*_f32 become compact rows d_out_dets [<= B*max_det, 6] = [cls, conf, x1, y1, x2, y2]
+ * (:96) with CSR offsets d_out_det_off [B+1]; the labels [T,6] = [image, cls, xc, yc, w, h] (normalised) become
+ * d_out_gts [<= T, 5] = [cls, x1, y1, x2, y2] in pixels (:98-99), grouped by image in input order, with d_out_gt_off [B+1].
+ * Both outputs have capacity shapes; only the offsets say how many rows are valid (feed them to fvb_map_match_f32 with
+ * total_dets = B*max_det).  A negative d_cnt[b] (failed image) counts as 0 detections.
+ */
+int fvb_val_evidence_f32(const float* d_boxes, const float* d_scores, const int64_t* d_cls, const int32_t* d_cnt, int batch,
+                         int max_det, const float* d_labels, int64_t num_labels, float img_w, float img_h,
+                         float* d_out_dets, int32_t* d_out_det_off, float* d_out_gts, int32_t* d_out_gt_off, void* stream);
 
 /* ---- debug hooks -------------------------------------------------------------------------------
  * NOT part of the product path and NOT thread-safe: process-global state, used by tools/ only.

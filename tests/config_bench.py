@@ -78,6 +78,11 @@ for i0 in range(0, args.map_images, args.map_batch):
         goff.append(goff[-1] + tj.size(0))
     gts = torch.cat(gts).cuda()
     goff = torch.tensor(goff, dtype=torch.int32, device="cuda")
+    if i0 == 0:
+        # untimed first call on a throw-away accumulator: it pays the workspace allocation (a cudaMalloc between the two events
+        # made round 1's "match_ms_total" read 390 ms for 20 launches that ncu times at 22 us each)
+        CalculateMAP(thr).process_batch(dets, det_off, gts, goff)
+        torch.cuda.synchronize()
     a, b = events()
     a.record()
     est.process_batch(dets, det_off, gts, goff)

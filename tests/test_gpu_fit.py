@@ -104,3 +104,123 @@ def test_fit_val_matches_oracle_pipeline():
     assert ids == w_ids
     np.testing.assert_allclose(m_iou, w_iou, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(m_cls, w_cls, rtol=1e-9, atol=1e-12)
+
+
+class _Backbone(nn.Module):
+    """Stand-in with the constructor / accessor contract fastvision's darknet53 offers to Yolov3 (classfication/models/darknet53.py)."""
+
+    def __init__(self, in_channels=3, including_top=False):
+        super().__init__()
+        self.convs = nn.ModuleList([nn.Conv2d(in_channels, 8, 1) for _ in SMALL.strides])
+
+    def backbone_strides_per_level(self):
+        return list(SMALL.strides)
+
+    def backbone_channels_per_level(self):
+        return [8 for _ in SMALL.strides]
+
+    def forward(self, x):
+        return [conv(F.avg_pool2d(x, int(s))) for s, conv in zip(SMALL.strides, self.convs)]
+
+
+class _Neck(nn.Module):
+    def __init__(self, feature_channels):
+        super().__init__()
+
+    def forward(self, feats):
+        return feats
+
+
+class _Head(nn.Module):
+    """[B, A, H, W, 5 + C] per level, like detection/head/yolov3head.py:52-67."""
+
+    def __init__(self, feature_channels, num_levels, num_anchors_per_level, num_classes):
+        super().__init__()
+        self.a, self.k = num_anchors_per_level, 5 + num_classes
+        self.convs = nn.ModuleList([nn.Conv2d(c, a * self.k, 1) for c, a in zip(feature_channels, num_anchors_per_level)])
+
+    def forward(self, feats):
+        out = []
+        for f, conv, a in zip(feats, self.convs, self.a):
+            y = conv(f)
+            b, _, h, w = y.shape
+            out.append(y.view(b, a, self.k, h, w).permute(0, 1, 3, 4, 2).contiguous())
+        return out
+
+
+def test_fit_val_with_the_package_yolov3_in_eval_mode():
+    """Fit._val with fastvision_b200.detection.models.Yolov3: after model.eval() its forward returns the TUPLE (head_out, results)
+    like the reference's (detection/models/yolov3.py:33-54); _val must unpack it, must not decode twice, and must reproduce the
+    oracle pipeline on the heads -- including with labels that do NOT arrive grouped by image."""
+    from fastvision_b200.detection.models import Yolov3
+    cfg = SMALL
+    torch.manual_seed(3)
+    anchors = torch.tensor(cfg.anchors_px, dtype=torch.float32)
+    model = Yolov3(_Backbone, _Neck, _Head, anchors, [cfg.anchors_per_level] * cfg.levels, num_classes=cfg.num_classes).cuda()
+    with torch.no_grad():
+        for conv in model.head.convs:
+            conv.bias.view(cfg.anchors_per_level, cfg.k)[:, 4] += 1.5
+    loader = make_loader(cfg, 2, 5, 21)
+    images, labels = loader[1]
+    loader[1] = (images, labels[torch.randperm(labels.size(0), generator=torch.Generator().manual_seed(1))])   # ungrouped labels
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    fit = Fit(model, torch.device("cuda"), opt, torch.optim.lr_scheduler.StepLR(opt, 1), Yolov3Loss(model, 0.5, 0.05, 1.0, 0.5),
+              end_epoch=1, train_loader=loader, val_loader=loader, verbose=False)
+    calls = []
+    orig = model.decode
+    model.decode = lambda h: (calls.append(1), orig(h))[1]
+    loss, m_iou, m_cls, ids = fit._val()
+    assert not calls and model.decode_in_forward is True        # no redundant decode, flag restored
+    model.eval()
+    out = model(loader[0][0].cuda())
+    assert isinstance(out, tuple) and out[1] is not None and out[1].size(1) == cfg.cells      # the reference's eval contract
+    thr = np.linspace(0.5, 0.95, 10)
+    est = oracle.map_.MapOracle(thr)
+    last = None
+    with torch.no_grad():
+        for images, labels in loader:
+            heads = [h.cpu() for h in model(images.cuda())[0]]
+            last = oracle.loss.yolov3_loss(heads, labels, cfg.anchors_levels(), cfg.strides)
+            res = oracle.decode.decode(heads, cfg.anchors_levels(), cfg.strides)
+            for i in range(images.size(0)):                                                   # utils/fit.py:93-101
+                s, c, b = oracle.nms.nms_lib(res[i], 0.25, 0.45, 300)
+                pred = torch.cat([c.float(), s, b], 1) if s.numel() else torch.zeros(0, 6)
+                est.process_one(pred, synth.labels_to_pixel_targets(labels, i, cfg.img, cfg.img))
+    w_iou, w_cls, w_ids = est.fetch()
+    np.testing.assert_allclose(loss, float(last), rtol=1e-5)
+    assert ids == w_ids
+    np.testing.assert_allclose(m_iou, w_iou, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(m_cls, w_cls, rtol=1e-9, atol=1e-12)
+
+
+def test_map_matcher_many_targets_and_padded_batches():
+    """More targets per image than the matcher stages in shared memory (1024) take the global-memory path; process_padded
+    (capacity-shaped evidence, counts read once at fetch) accumulates the same rows as process_batch on exact tensors."""
+    from fastvision_b200.metrics import CalculateMAP
+    g = torch.Generator().manual_seed(5)
+    thr = np.linspace(0.5, 0.95, 10)
+    n_t, n_d = 1500, 260
+    tb = torch.rand(n_t, 2, generator=g) * 380
+    gts = torch.cat([torch.randint(0, 3, (n_t, 1), generator=g).float(), tb, tb + torch.rand(n_t, 2, generator=g) * 30 + 4], 1)
+    src = torch.randint(0, n_t, (n_d,), generator=g)
+    dets = torch.cat([gts[src, 0:1], torch.rand(n_d, 1, generator=g), gts[src, 1:] + torch.randn(n_d, 4, generator=g) * 1.5], 1)
+    dets[5] = dets[4]
+    eo, eg = oracle.map_.MapOracle(thr), CalculateMAP(thr)
+    eo.process_one(dets, gts)
+    eg.process_one(dets.cuda(), gts.cuda())
+    assert np.array_equal(eo.correct_all_images[-1], eg.correct_all_images[-1])
+    # padded path == exact path on a ValStep output
+    cfg, batch = SMALL, 6
+    gg = synth.make_generator(1, rank=5)
+    labels = synth.make_labels(cfg, batch, gg)
+    heads = [h.cuda() for h in synth.make_heads(cfg, batch, labels, gg)]
+    from fastvision_b200.pipeline import ValStep
+    step = ValStep(cfg.anchors_levels(), cfg.strides)
+    o = step(heads, labels.cuda())
+    a, b = CalculateMAP(thr), CalculateMAP(thr)
+    a.process_padded(o["boxes"], o["scores"], o["cls"], o["cnt"], labels.cuda(), cfg.img, cfg.img)
+    for i, d in enumerate(step.detections()):
+        b.process_one(d, synth.labels_to_pixel_targets(labels, i, cfg.img, cfg.img).cuda())
+    ra, rb = a.fetch(), b.fetch()
+    assert ra[2] == rb[2] and np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    assert np.array_equal(np.concatenate(a.correct_all_images), np.concatenate(b.correct_all_images))
