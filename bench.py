@@ -623,6 +623,7 @@ def run_cuda(args, cfg):
         t_end.record()
         barrier()
     total_ms = t_begin.elapsed_time(t_end)
+    step.check()                                   # no NMS CTA timed out, no failed peer reduction during the timed region
     decode_ms = [ev_d0[i].elapsed_time(ev_d1[i]) for i in sampled]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if distributed:

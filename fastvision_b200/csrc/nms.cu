@@ -323,19 +323,27 @@ struct SegNmsParams {
   int* keep_cnt;
   unsigned long long* ws_keys;  // [2 * total]
   float4* ws_box;               // [total]
+  // kept list of long keeps (max_keep > kKeepSmem): global memory, segment s owns entries [seg_off[s], seg_off[s+1])
+  float4* ws_kbox;              // [total]
+  float* ws_karea;              // [total]
+  int* ws_kslot;                // [total]
 };
+
+constexpr int kKeepSmem = 4096;  // kept entries (24 B each) held in shared memory; longer keeps live in the workspace
 
 __global__ void __launch_bounds__(kNmsThreads) seg_nms_kernel(const SegNmsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const NmsSmemLayout L = nms_layout(kCapS, p.max_keep);
+  const bool keep_in_smem = p.max_keep <= kKeepSmem;
+  const NmsSmemLayout L = nms_layout(kCapS, keep_in_smem ? p.max_keep : 0);
   const int s = blockIdx.x;
   uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L.cnt);
   uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + L.warp_tot);
-  float4* kbox = reinterpret_cast<float4*>(smem + L.kbox);
-  float* karea = reinterpret_cast<float*>(smem + L.karea);
-  int* kslot = reinterpret_cast<int*>(smem + L.kslot);
   GreedyShared* gs = reinterpret_cast<GreedyShared*>(smem + L.gs);
   const int beg = p.seg_off[s], n = p.seg_off[s + 1] - beg;
+  // a segment never keeps more than its own n boxes, so its slice [beg, beg + n) of the workspace arrays always suffices
+  float4* kbox = keep_in_smem ? reinterpret_cast<float4*>(smem + L.kbox) : p.ws_kbox + beg;
+  float* karea = keep_in_smem ? reinterpret_cast<float*>(smem + L.karea) : p.ws_karea + beg;
+  int* kslot = keep_in_smem ? reinterpret_cast<int*>(smem + L.kslot) : p.ws_kslot + beg;
   if (n <= 0) {
     if (threadIdx.x == 0) p.keep_cnt[s] = 0;
     return;
@@ -522,7 +530,9 @@ extern "C" int fvb_yolo_nms_after_decode_f32(const float* d_results, int batch, 
 
 extern "C" size_t fvb_nms_segmented_workspace_bytes(int64_t total_boxes, int segments) {
   (void)segments;
-  return align_up((size_t)total_boxes * 16, 256) + align_up((size_t)total_boxes * 16, 256) + 256;
+  const size_t t = (size_t)total_boxes;
+  return align_up(t * 16, 256) /* keys x2 */ + align_up(t * 16, 256) /* boxes */ + align_up(t * 16, 256) /* kept boxes */ +
+         2 * align_up(t * 4, 256) /* kept areas, slots */ + 256;
 }
 
 extern "C" int fvb_nms_segmented_f32(const float* d_boxes, const float* d_scores, const int32_t* d_seg_offsets,
@@ -541,9 +551,16 @@ extern "C" int fvb_nms_segmented_f32(const float* d_boxes, const float* d_scores
   p.max_keep = max_keep;
   p.keep_idx = d_keep_idx;
   p.keep_cnt = d_keep_cnt;
-  p.ws_keys = (unsigned long long*)d_ws;
-  p.ws_box = (float4*)((unsigned char*)d_ws + align_up((size_t)total_boxes * 16, 256));
-  NmsSmemLayout L = nms_layout(kCapS, max_keep);
+  {
+    unsigned char* w = (unsigned char*)d_ws;
+    const size_t t = (size_t)total_boxes;
+    p.ws_keys = (unsigned long long*)w;  w += align_up(t * 16, 256);
+    p.ws_box = (float4*)w;               w += align_up(t * 16, 256);
+    p.ws_kbox = (float4*)w;              w += align_up(t * 16, 256);
+    p.ws_karea = (float*)w;              w += align_up(t * 4, 256);
+    p.ws_kslot = (int*)w;
+  }
+  NmsSmemLayout L = nms_layout(kCapS, max_keep <= kKeepSmem ? max_keep : 0);
   int rc = ensure_smem((const void*)seg_nms_kernel, L.total, "nms_segmented");
   if (rc != FVB_OK) return rc;
   seg_nms_kernel<<<segments, kNmsThreads, L.total, (cudaStream_t)stream>>>(p);

@@ -6,7 +6,9 @@
 // publish my partials into slot e&1 of MY buffer, release-store flag = e, acquire-spin on every peer's flag, then every rank
 // sums the W vectors in rank order -- bit-identical results on all ranks -- and forms the loss with the global-batch
 // normalisers.  Slot reuse is safe: a rank reaches epoch e+2 only after all peers published e+1, i.e. finished reading e.
-// A peer that never arrives trips a ~10 s timeout: status := 1, loss := NaN (no hang).
+// A peer that never arrives trips a ~10 s timeout: status := 1, loss := NaN (no hang); a flag from a LATER epoch (a peer that ran
+// on after somebody's timeout and re-used the slot) gives status := 2, loss := NaN.  The status word is sticky;
+// dist.PeerReducer.raise_if_failed() surfaces it.
 #include "common.cuh"
 
 namespace fvb {
@@ -80,20 +82,27 @@ __global__ void __launch_bounds__(32) peer_reduce_combine_kernel(const PeerParam
     if (tid == 0) mine->slot[s].vals[i] = v;
   }
   if (tid == 0) st_release_sys(&mine->slot[s].flag, e);
-  // wait for every peer's epoch-e publication (lane <-> peer)
-  bool ok = true;
+  // wait for every peer's epoch-e publication (lane <-> peer).  The flag must end up EXACTLY e: a larger value means that peer
+  // has already re-used the slot for epoch e+2 (only possible after somebody timed out), i.e. the values are not epoch e's.
+  int ok_code = 0;  // 0 ok, 1 timeout, 2 desynchronised
   if (tid < p.world && tid != p.rank) {
     const PeerBuf* pb = reinterpret_cast<const PeerBuf*>(p.peers[tid]);
     const long long t0 = clock64();
-    while (ld_acquire_sys(&pb->slot[s].flag) < e) {
+    unsigned long long f;
+    while ((f = ld_acquire_sys(&pb->slot[s].flag)) < e) {
       if (clock64() - t0 > 20000000000ll) {  // ~10 s: a rank is missing -- give up instead of hanging the GPU
-        ok = false;
+        ok_code = 1;
         break;
       }
       __nanosleep(100);
     }
+    if (ok_code == 0 && f != e) ok_code = 2;
   }
-  ok = __all_sync(0xffffffffu, ok);
+  const bool ok = __all_sync(0xffffffffu, ok_code == 0);
+  const bool timed_out = __any_sync(0xffffffffu, ok_code == 1);
+  // vote.sync is not a memory barrier: lane T reads values that lane L's acquire made visible, so order them with the
+  // warp-level barrier (memory ordering among the participating lanes)
+  __syncwarp();
   if (tid < p.n) {
     double acc = 0.0;
     for (int r = 0; r < p.world; ++r)  // rank order: the same bits on every rank
@@ -103,7 +112,7 @@ __global__ void __launch_bounds__(32) peer_reduce_combine_kernel(const PeerParam
   }
   __syncwarp();
   if (tid == 0) {
-    if (p.status) p.status[0] = ok ? 0 : 1;
+    if (p.status && !ok) p.status[0] = timed_out ? 1 : 2;  // sticky: once a reduction failed the buffer stays marked
     p.out_loss[0] = ok ? peer_combine(p.g, s_sum, p.batch_global, p.r_box, p.r_conf, p.r_cls)
                        : __int_as_float(0x7fc00000);
   }

@@ -123,8 +123,9 @@ def nms(boxes, scores, iou_threshold, seg_offsets=None, max_keep=None):
     if max_keep is None:
         max_keep = max(n, 1) if single else 2000
     lib = _lib.load()
-    # the kept list lives in shared memory: split very long keeps into what fits (~7000 entries)
-    max_keep = min(int(max_keep), 7000)
+    # never truncates: a single segment may keep all n boxes (as torchvision.ops.nms does); kept lists longer than what fits
+    # in shared memory live in the workspace (csrc/nms.cu: kKeepSmem)
+    max_keep = max(1, int(max_keep))
     keep = torch.empty(segs, max_keep, dtype=torch.int32, device=dev)
     cnt = torch.empty(segs, dtype=torch.int32, device=dev)
     ws = _lib.workspace(lib.fvb_nms_segmented_workspace_bytes(n, segs), dev, "seg_nms")

@@ -105,6 +105,15 @@ class PeerReducer:
                                                             _lib.dptr(partials), _lib.dptr(out_loss), _lib.dptr(self.status),
                                                             _lib.stream()), "loss_peer_combine")
 
+    def raise_if_failed(self):
+        """Host check of the sticky status word of the peer reductions (one 4-byte D2H read: call it where the loss is read
+        anyway).  1 = a rank did not arrive within ~10 s, 2 = ranks desynchronised; either way the losses since are NaN."""
+        code = int(self.status.item())
+        if code:
+            raise RuntimeError("fastvision_b200: peer-memory loss reduction failed (status %d: %s) on rank %d" %
+                               (code, "a rank did not arrive" if code == 1 else "ranks desynchronised", self.rank))
+
+
 
 def peer_reducer(device, group=None) -> Optional["PeerReducer"]:
     """The process-wide PeerReducer of ``group`` (created collectively on first use), or None when symmetric memory is not
@@ -114,10 +123,20 @@ def peer_reducer(device, group=None) -> Optional["PeerReducer"]:
         return None
     key = (id(group), device.index)
     if key not in _peer_reducers:
+        red, err = None, None
         try:
-            _peer_reducers[key] = PeerReducer(device, group)
+            red = PeerReducer(device, group)
         except Exception as exc:  # symmetric memory unsupported on this system: NCCL path
-            import warnings
-            warnings.warn("fastvision_b200: peer-memory reduce unavailable (%s); using NCCL all-reduce" % (exc,))
-            _peer_reducers[key] = None
+            err = exc
+        # the choice must be the SAME on every rank (one rank on NCCL and the others in the peer kernel would wait for each other
+        # forever): agree on the minimum of the success flags
+        agreed = torch.tensor([1 if red is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=group)
+        if int(agreed.item()) == 0:
+            if err is not None or red is not None:
+                import warnings
+                warnings.warn("fastvision_b200: peer-memory reduce unavailable on at least one rank (%s); all ranks use the NCCL "
+                              "all-reduce" % (err if err is not None else "another rank failed",))
+            red = None
+        _peer_reducers[key] = red
     return _peer_reducers[key]

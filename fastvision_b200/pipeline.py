@@ -207,6 +207,14 @@ class ValStep:
             return (lambda: (self._head(heads, labels), self._decode(heads))), g.replay
         return g.replay
 
+    def check(self):
+        """Host-side health check for the places where the caller reads results anyway (it syncs): raises if an image's NMS
+        gave up waiting for its decode (cnt < 0) or if a data-parallel peer reduction failed (loss is NaN then)."""
+        if self.out is not None and int(self.out["cnt"].min()) < 0:
+            raise RuntimeError("fastvision_b200: an overlapped NMS CTA timed out waiting for the decode kernel (cnt = -1)")
+        if self._distributed() and self._peer_reducer not in (False, None):
+            self._peer_reducer.raise_if_failed()
+
     def detections(self, out=None):
         """Ragged per-image detections [k,6] = [cls, conf, x1, y1, x2, y2] (the layout utils/fit.py:96 builds). Syncs."""
         o = out or self.out

@@ -214,6 +214,20 @@ def test_nms_segmented_batched_and_large():
         assert np.array_equal(got, want), (i, n)
 
 
+def test_nms_single_segment_keeps_more_than_shared_memory_holds():
+    """``nms(boxes, scores, thr)`` is the torchvision call: it returns EVERY survivor.  12 000 sparse boxes keep ~10 000 -- far
+    more than the kept list's shared-memory capacity -- and 20 000 clustered ones exercise the long sort + long keep together."""
+    gen = torch.Generator().manual_seed(77)
+    for n, spread, thr in ((12000, 4000.0, 0.5), (20000, 600.0, 0.6)):
+        xy = torch.rand(n, 2, generator=gen) * spread
+        boxes = torch.cat([xy, xy + torch.rand(n, 2, generator=gen) * 40 + 2], 1)
+        scores = torch.rand(n, generator=gen)
+        want = on.nms_greedy(boxes, scores, thr)
+        got = ft.nms(boxes.cuda(), scores.cuda(), thr).cpu()
+        assert got.numel() == want.numel() and want.numel() > 4096, (n, got.numel(), want.numel())
+        assert torch.equal(got, want)
+
+
 def test_nms_segmented_sort_boundaries_and_score_ties():
     """Every size class of the in-kernel sort (bitonic network: 64..1024 keys at 2 per thread, 2048 at 4 per thread; radix
     beyond) with scores drawn from a handful of values, so the order is decided by the tie rule (lower index first)."""
