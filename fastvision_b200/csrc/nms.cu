@@ -64,7 +64,7 @@ struct NmsSmemLayout {
   size_t keys0, box, row, cnt, warp_tot, kbox, karea, kslot, gs, misc, total;
 };
 
-__host__ __device__ inline NmsSmemLayout nms_layout(int cap, int max_keep) {
+__host__ __device__ inline NmsSmemLayout nms_layout(int cap, int max_keep, int kNmsWarps = fvb::kNmsWarps) {
   NmsSmemLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes, size_t align) {
@@ -87,8 +87,10 @@ __host__ __device__ inline NmsSmemLayout nms_layout(int cap, int max_keep) {
   return L;
 }
 
+template <int NT>
 __device__ __forceinline__ void yolo_nms_image(const YoloNmsParams& p, const int b, unsigned char* smem) {
-  const NmsSmemLayout L = nms_layout(kCapS, p.max_det);
+  constexpr int kNmsWarps = NT / 32, kNmsThreads = NT;  // shadow the namespace constants inside this function
+  const NmsSmemLayout L = nms_layout(kCapS, p.max_det, kNmsWarps);
   const int lane = threadIdx.x & 31;
   uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + L.cnt);
   uint32_t* warp_tot = reinterpret_cast<uint32_t*>(smem + L.warp_tot);
@@ -106,7 +108,7 @@ __device__ __forceinline__ void yolo_nms_image(const YoloNmsParams& p, const int
   const int wbeg = min(p.words, (int)threadIdx.x * wpt), wend = min(p.words, wbeg + wpt);
   uint32_t my = 0;
   for (int w = wbeg; w < wend; ++w) my += __popc(bm[w]);
-  uint32_t base = block_exclusive_scan(my, warp_tot);
+  uint32_t base = block_exclusive_scan<NT>(my, warp_tot);
   const int n = (int)warp_tot[kNmsWarps];
   __syncthreads();  // warp_tot is reused by the sort
 
@@ -181,11 +183,11 @@ __device__ __forceinline__ void yolo_nms_image(const YoloNmsParams& p, const int
   if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 2] = gtime_ns();
   unsigned long long* sorted = keys0;
   if (n <= kCapS)
-    block_bitonic_sort64(keys0, n);
+    block_bitonic_sort64<NT>(keys0, n);
   else
-    sorted = block_radix_sort_hi32(keys0, keys1, n, cnt, warp_tot);
+    sorted = block_radix_sort_hi32<NT>(keys0, keys1, n, cnt, warp_tot);
   if (p.trace && threadIdx.x == 0) p.trace[b * 8 + 3] = gtime_ns();
-  int kept = block_greedy_nms(sorted, n_use, sbox, p.iou_thr, p.max_det, kbox, karea, kslot, gs);
+  int kept = block_greedy_nms<NT>(sorted, n_use, sbox, p.iou_thr, p.max_det, kbox, karea, kslot, gs);
   if (p.trace && threadIdx.x == 0) { p.trace[b * 8 + 4] = gtime_ns(); p.trace[b * 8 + 6] = n; p.trace[b * 8 + 7] = kept; }
 
   // ---- phase 4: padded outputs -------------------------------------------------------------------------------
@@ -214,8 +216,11 @@ __device__ __forceinline__ void yolo_nms_image(const YoloNmsParams& p, const int
 // waits until its image's tiles are all published -- one thread polls with an acquire load, the others sleep in the
 // barrier -- and then runs the image's NMS while the decode kernel is still streaming the later images.  Only the images
 // decoded last are left when the decode kernel exits, so the step's tail is one image's NMS latency instead of a whole wave's.
-template <bool PDL>
-__global__ void __maxnreg__(40) yolo_nms_kernel(const YoloNmsParams p) {
+// NT = 512: 40 registers, so that a CTA fits beside a decode CTA (and two fit an SM).  NT = 1024 (plain launches of at most one
+// image per SM -- small batches, e.g. a data-parallel shard): twice the warps on the SM the image has to itself anyway; the
+// greedy loop is latency-bound (~0.4 instructions per cycle per scheduler with 4 warps each), so its chunks go ~1.6x faster.
+template <bool PDL, int NT>
+__global__ void __maxnreg__(NT == 512 ? 40 : 64) yolo_nms_kernel(const YoloNmsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.x;
   bool ok = true;
@@ -240,7 +245,7 @@ __global__ void __maxnreg__(40) yolo_nms_kernel(const YoloNmsParams p) {
     __syncthreads();  // (cumulativity: thread 0's acquire + this barrier order every thread's reads after the decode's writes)
     ok = s_ok != 0;
   }
-  if (ok) yolo_nms_image(p, b, smem);
+  if (ok) yolo_nms_image<NT>(p, b, smem);
   else if (threadIdx.x == 0) p.out_cnt[b] = -1;
   if (PDL) {
     // The grid after this one in the stream must not start before the DECODE grid has fully exited (it re-arms its tile queue
@@ -500,13 +505,23 @@ extern "C" int fvb_yolo_nms_after_decode_f32(const float* d_results, int batch, 
   p.tiles_per_image = (unsigned)tiles_per_image;
   NmsSmemLayout L = nms_layout(kCapS, max_det);
   if (d_tile_sync == nullptr) {
-    int rc = ensure_smem((const void*)yolo_nms_kernel<false>, L.total, "yolo_nms");
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+    if (batch <= sms) {  // every image has an SM to itself: 1024 threads per image
+      const NmsSmemLayout L2 = nms_layout(kCapS, max_det, 32);
+      int rc = ensure_smem((const void*)yolo_nms_kernel<false, 1024>, L2.total, "yolo_nms");
+      if (rc != FVB_OK) return rc;
+      yolo_nms_kernel<false, 1024><<<batch, 1024, L2.total, cs>>>(p);
+      count_launch();
+      return check_launch("yolo_nms_kernel<1024>");
+    }
+    int rc = ensure_smem((const void*)yolo_nms_kernel<false, 512>, L.total, "yolo_nms");
     if (rc != FVB_OK) return rc;
-    yolo_nms_kernel<false><<<batch, kNmsThreads, L.total, cs>>>(p);
+    yolo_nms_kernel<false, 512><<<batch, kNmsThreads, L.total, cs>>>(p);
     count_launch();
     return check_launch("yolo_nms_kernel");
   }
-  int rc = ensure_smem((const void*)yolo_nms_kernel<true>, L.total, "yolo_nms_after_decode");
+  int rc = ensure_smem((const void*)yolo_nms_kernel<true, 512>, L.total, "yolo_nms_after_decode");
   if (rc != FVB_OK) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)batch);
@@ -518,7 +533,7 @@ extern "C" int fvb_yolo_nms_after_decode_f32(const float* d_results, int batch, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, yolo_nms_kernel<true>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, yolo_nms_kernel<true, 512>, p);
   if (e != cudaSuccess) {
     set_error("yolo_nms_after_decode: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

@@ -10,7 +10,7 @@ from fastvision_b200 import synth, _lib  # noqa: E402
 from fastvision_b200.detection.models import yolov3_decode, DecodeContext  # noqa: E402
 from fastvision_b200.detection.tools import non_max_suppression_batched  # noqa: E402
 
-cfg = synth.COCO416
+cfg = synth.CONFIGS[os.environ.get("CFG", "yolov3-416-coco")]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 g = synth.make_generator(2)
 labels = synth.make_labels(cfg, B, g)
