@@ -803,8 +803,9 @@ def run_cuda(args, cfg):
                        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2; no flush needed" % (alg_bytes / 2e6),
                        "step_launch": step_launch,
                        "pipelined_extra": {"ms_per_step": pipelined_ms, "images_per_s": batch * world / (pipelined_ms * 1e-3), "steps": kp,
-                                           "note": "ValPipeline: NMS + loss of batch i overlap the decode of batch i+1 (two buffer sets); "
-                                                   "not the headline because the co-running tail slows the decode kernel"}},
+                                           "note": "ValPipeline: two ValSteps on alternating streams -- batch i+1's decode waits only for batch i's "
+                                                   "decode kernel, so the ~40 us left of batch i (NMS of its last images, loss finish) runs under it; "
+                                                   "not the headline: the K steps of the headline do not overlap one another"}},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": ke, "serial_value": e2e_serial,

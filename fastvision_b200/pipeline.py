@@ -224,101 +224,68 @@ class ValStep:
 
 
 class ValPipeline:
-    """Software-pipelined validation loop: the NMS + loss tail of batch i overlaps the decode of batch i+1.
+    """Software-pipelined validation loop: what is left of batch i after its decode overlaps the decode of batch i+1.
 
-    ``Fit._val`` (utils/fit.py:86-105) walks the validation set batch by batch; nothing in batch i+1's decode
-    depends on batch i's detections, so the latency-bound NMS (one CTA per image) and the tiny loss kernels run
-    on two side streams while the main stream already streams the next batch through the (HBM-bound, persistent)
-    decode kernel, which leaves shared memory for one NMS CTA per SM.  Two buffer sets (results, candidate bitmap /
-    records, objectness partials, padded detections, loss) alternate; ``submit`` waits on the events of the set
-    it is about to overwrite, so outputs of batch i stay valid until batch i+2 is submitted.
-    Under ``torch.distributed`` the 96-byte all-reduce of the loss partials sits in the loss branch.
+    ``Fit._val`` (utils/fit.py:86-105) walks the validation set batch by batch; nothing in batch i+1's decode depends on batch
+    i's detections.  Every ``ValStep`` already runs each image's NMS under its own decode kernel; what remains at the end of a
+    step is the NMS of the images decoded last (~40 us) and the loss finish.  Here ``depth`` ValSteps (own buffers, own
+    streams) alternate: batch i+1's decode waits only for batch i's DECODE kernel (two persistent decode kernels would just
+    fight for the SMs), not for its tail, which therefore runs under the next decode.  ``submit`` returns the slot's output
+    buffers; they are valid after ``wait(slot)`` / ``flush()`` and stay so until the slot is submitted again.
     """
 
     def __init__(self, anchors_per_level, strides, depth=2, **kw):
-        kw = dict(kw, overlap_nms=False)     # decode and NMS sit on different streams here: plain (stream-ordered) launches
         self.steps = [ValStep(anchors_per_level, strides, **kw) for _ in range(depth)]
         self.depth = depth
         self.count = 0
-        self._dec_stream = None
-        self._nms_stream = None
-        self._loss_stream = None
-        self._done = [None] * depth
+        self._streams = None
+        self._done = None
+        self._ev_in = None
 
-    def _streams(self, dev):
-        if self._nms_stream is None:
-            lo, hi = torch.cuda.Stream.priority_range()      # (least, greatest) = (0, -k)
-            # the decode grid (one persistent CTA per SM) must be placed first; NMS CTAs then take the shared memory
-            # it leaves (one per SM).  With the priorities the other way round two NMS CTAs per SM would lock the
-            # decode out until they finish -- no overlap at all.
-            self._dec_stream = torch.cuda.Stream(device=dev, priority=hi)
-            self._nms_stream = torch.cuda.Stream(device=dev, priority=lo)
-            self._loss_stream = torch.cuda.Stream(device=dev, priority=lo)
-            self._done = [(torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()) for _ in range(self.depth)]
+    def _prepare(self, dev):
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.depth)]
+            self._done = [torch.cuda.Event() for _ in range(self.depth)]
             self._ev_in = [torch.cuda.Event() for _ in range(self.depth)]
-        return self._dec_stream, self._nms_stream, self._loss_stream
 
-    def submit(self, head_out: List[torch.Tensor], labels: torch.Tensor, decode_events=None, trace=None):
+    def submit(self, head_out: List[torch.Tensor], labels: torch.Tensor, decode_events=None):
         """Enqueue one batch; returns the dict of output buffers of this slot (valid after ``wait(slot)``/``flush``).
 
         ``decode_events``: optional (start, stop) CUDA events recorded around the decode kernel on its stream.
-        ``trace``: optional dict name -> (start, stop) timing events for "nms" / "loss" (tools/pipeline_trace.py).
         """
         slot = self.count % self.depth
         st = self.steps[slot]
         heads = [_lib.require_cuda(h, "head_out[%d]" % i) for i, h in enumerate(head_out)]
         labels = _lib.require_cuda(labels, "labels").view(-1, 6)
         st._prepare(heads)
-        dec_s, nms_s, loss_s = self._streams(st.ctx.device)
-        ev_dec, ev_nms, ev_loss = self._done[slot]
-        ev_in = self._ev_in[slot]
+        self._prepare(st.ctx.device)
+        stream, ev_in = self._streams[slot], self._ev_in[slot]
         ev_in.record(torch.cuda.current_stream())    # inputs are ready once the caller's stream gets here
-        o, ctx = st.out, st.ctx
-        with torch.cuda.stream(dec_s):
-            dec_s.wait_event(ev_in)
-            if self.count >= self.depth:             # the slot's previous tail must have consumed its buffers
-                dec_s.wait_event(ev_nms)
-                dec_s.wait_event(ev_loss)
+        with torch.cuda.stream(stream):
+            stream.wait_event(ev_in)
+            # (the slot's previous batch is older work on this same stream: its buffers are free by stream order)
+            if self.count > 0:
+                stream.wait_event(self.steps[(self.count - 1) % self.depth]._ev_decoded)   # the previous batch's decode kernel
+            st._head(heads, labels)
             if decode_events is not None:
-                decode_events[0].record(dec_s)
+                decode_events[0].record(stream)
             st._decode(heads)
             if decode_events is not None:
-                decode_events[1].record(dec_s)
-            ev_dec.record(dec_s)
-        with torch.cuda.stream(loss_s):
-            loss_s.wait_event(ev_dec)
-            if trace is not None:
-                trace["loss"][0].record(loss_s)
-            st.loss_fn(heads, labels, conf_bce0=ctx.bce0(), ctx=ctx, out=o["loss"], partials=o["partials"],
-                       conf_bce0_precise=st.precise)
-            st._reduce()
-            if trace is not None:
-                trace["loss"][1].record(loss_s)
-            ev_loss.record(loss_s)
-        with torch.cuda.stream(nms_s):
-            nms_s.wait_event(ev_dec)
-            if trace is not None:
-                trace["nms"][0].record(nms_s)
-            st._nms()
-            if trace is not None:
-                trace["nms"][1].record(nms_s)
-            ev_nms.record(nms_s)
+                decode_events[1].record(stream)
+            st._tail(heads, labels, reduce_inside=True)
+            self._done[slot].record(stream)
         self.count += 1
-        return o
+        return st.out
 
     def wait(self, slot=None):
-        """Make the current stream wait for the tail of ``slot`` (default: the most recently submitted batch)."""
+        """Make the current stream wait for the batch in ``slot`` (default: the most recently submitted one)."""
         if self.count == 0:
             return
         slot = (self.count - 1) % self.depth if slot is None else slot
-        ev_dec, ev_nms, ev_loss = self._done[slot]
-        main = torch.cuda.current_stream()
-        main.wait_event(ev_dec)
-        main.wait_event(ev_nms)
-        main.wait_event(ev_loss)
+        torch.cuda.current_stream().wait_event(self._done[slot])
 
     def flush(self):
-        """Join every outstanding tail into the current stream."""
+        """Join every outstanding batch into the current stream."""
         for slot in range(min(self.count, self.depth)):
             self.wait(slot)
 
