@@ -436,7 +436,9 @@ __device__ __forceinline__ void process_tile(const DecodeParams& p, const Tile& 
   }
 }
 
-template <int NSB, int FORM, bool PRECISE>
+// PUB: publish per-image progress (p.tile_done) for the overlapped NMS.  A template parameter, not a run-time test: the three
+// counters it needs pushed the 64-row-tile instantiation (narrow rows, which never publish) into register spills.
+template <int NSB, int FORM, bool PRECISE, bool PUB>
 __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const DecodeParams p) {
   extern __shared__ __align__(16) float dec_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
     if (p.g.nchw) issue_tile_nchw<NSB>(p, cur, buf, lane);
     else issue_tile(cur, buf, lane);
     cp_async_commit();
-    if (pub_n) {
+    if (PUB && pub_n) {
       // the previous batch's publication, deferred to here: its fence waits for that batch's stores to be acknowledged --
       // with this tile's loads already in flight behind it the warp loses nothing (at the batch's end it cost ~1 us per batch)
       publish_tiles(p, pend_b, pub_n, lane);
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
     __syncwarp();  // every lane's copies have landed
     process_tile<NSB, FORM, PRECISE>(p, cur, buf);
     __syncwarp();  // the buffer may be refilled
-    if (p.tile_done != nullptr) {
+    if (PUB) {
       // one publication per image per drawn batch (a batch is <= batch_max consecutive tiles, mostly of one image)
       if (cur.b != pend_b) {  // crossed into another image (rare): the old image's count goes out now
         publish_tiles(p, pend_b, pend_n, lane);
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(kDecodeMaxThreads, 1) decode_kernel(const Deco
     }
     ++u;
   }
-  if (p.tile_done != nullptr) publish_tiles(p, pend_b, pub_n + pend_n, lane);
+  if (PUB) publish_tiles(p, pend_b, pub_n + pend_n, lane);
   if (p.trace != nullptr && lane == 0) {
     long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -636,25 +638,32 @@ int make_geom(const fvb_yolo_geom* g, const float* const* d_heads, Geom* out) {
   return FVB_OK;
 }
 
-template <int FORM, bool PRECISE>
-static int launch_decode(const DecodeParams& p, const DecodeShape& sh, cudaStream_t s) {
-  const int nsb = (p.tile_rows + 31) / 32;
-  const void* fn = nullptr;
-  if (nsb == 1) fn = (const void*)decode_kernel<1, FORM, PRECISE>;
-  else if (nsb == 2) fn = (const void*)decode_kernel<2, FORM, PRECISE>;
-  else fn = (const void*)decode_kernel<4, FORM, PRECISE>;
+template <int NSB, int FORM, bool PRECISE, bool PUB>
+static int launch_decode_inst(const DecodeParams& p, const DecodeShape& sh, cudaStream_t s) {
+  const void* fn = (const void*)decode_kernel<NSB, FORM, PRECISE, PUB>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem_bytes);
-  // Ask for the largest shared-memory carve-out: the SM partition is fixed while a CTA is resident, and the NMS CTA that joins
-  // this one (programmatic dependent, or the previous batch's tail) needs its 82 KB next to our ~109 KB.
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  // Ask for the largest shared-memory carve-out when an NMS CTA can join this one (programmatic dependent, or the previous
+  // batch's tail): the SM partition is fixed while a CTA is resident, and the NMS CTA needs its 82 KB next to our ~109 KB.
+  // Not otherwise: narrow rows (24 warps, no room for an NMS CTA anyway) lose 4.5 % to the smaller L1 (608 / C=10 / B=1024:
+  // fused decode 0.550 -> 0.585 ms).
+  const bool room = sh.warps_per_cta * 32 * 64 + 512 * 40 <= 65536;
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, room ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
   if (e != cudaSuccess) {
     set_error("decode: cudaFuncSetAttribute(%zu): %s", sh.smem_bytes, cudaGetErrorString(e));
     return FVB_E_CUDA;
   }
-  if (nsb == 1) decode_kernel<1, FORM, PRECISE><<<sh.grid, 32 * sh.warps_per_cta, sh.smem_bytes, s>>>(p);
-  else if (nsb == 2) decode_kernel<2, FORM, PRECISE><<<sh.grid, 32 * sh.warps_per_cta, sh.smem_bytes, s>>>(p);
-  else decode_kernel<4, FORM, PRECISE><<<sh.grid, 32 * sh.warps_per_cta, sh.smem_bytes, s>>>(p);
+  decode_kernel<NSB, FORM, PRECISE, PUB><<<sh.grid, 32 * sh.warps_per_cta, sh.smem_bytes, s>>>(p);
   return FVB_OK;
+}
+
+template <int FORM, bool PRECISE>
+static int launch_decode(const DecodeParams& p, const DecodeShape& sh, cudaStream_t s) {
+  const int nsb = (p.tile_rows + 31) / 32;
+  const bool pub = p.tile_done != nullptr;
+  if (nsb == 1) return pub ? launch_decode_inst<1, FORM, PRECISE, true>(p, sh, s) : launch_decode_inst<1, FORM, PRECISE, false>(p, sh, s);
+  if (nsb == 2) return pub ? launch_decode_inst<2, FORM, PRECISE, true>(p, sh, s) : launch_decode_inst<2, FORM, PRECISE, false>(p, sh, s);
+  return pub ? launch_decode_inst<4, FORM, PRECISE, true>(p, sh, s) : launch_decode_inst<4, FORM, PRECISE, false>(p, sh, s);
 }
 
 }  // namespace fvb
