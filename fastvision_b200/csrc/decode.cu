@@ -580,10 +580,15 @@ int decode_launch_shape(const Geom& g, DecodeShape* s) {
   }
   s->stages = 1;
   const size_t per_warp = (size_t)s->tile_floats * sizeof(float);
-  int wpc = (int)(kDecodeSmemBudget / per_warp);
-  // narrow rows (K <= 21: 64-128 rows, < 8 KB per tile) carry more per-row work per byte: 24 warps hide it better (608 / C=10 /
-  // B=1024 with all side outputs: 0.557 ms at 20 warps, 0.512 at 24, 0.508 at 28); wide rows are best at 20 (0.304 vs 0.306 ms)
-  const int want = knob_warps() ? knob_warps() : (s->tile_rows >= 64 ? 24 : kDecodeWarps);
+  // Narrow rows (K <= 21: 64-128 rows, < 8 KB per tile) are bound by the bytes a CTA keeps in flight (one tile per warp) and by
+  // their denser per-row work: they take the whole SM -- 32 warps x 64 registers, up to 200 KB of tiles -- since more than 20
+  // warps leave no registers for an NMS CTA anyway.  608 / C=10, fused decode / whole step: 24 warps 0.540 / 0.721 ms at B=1024
+  // and 0.103 / 0.119 ms at B=128; 32 warps 0.523 / 0.705 and 0.101 / 0.114 (128-row tiles: slower at small batches).
+  // Wide rows are best at 20 warps (0.304 vs 0.306 ms) and keep the 112 KB budget that leaves room for an NMS CTA.
+  const bool narrow = s->tile_rows >= 64;
+  const size_t budget = narrow ? (size_t)200 * 1024 : kDecodeSmemBudget;
+  int wpc = (int)(budget / per_warp);
+  const int want = knob_warps() ? knob_warps() : (narrow ? 32 : kDecodeWarps);
   if (wpc > want) wpc = want;
   if (wpc < 1) {
     set_error("decode: K=%d rows do not fit the shared-memory tile", g.K);
