@@ -77,3 +77,41 @@ def test_shard_labels_rebases():
     labels = torch.tensor([[0, 1, .5, .5, .1, .1], [2, 3, .5, .5, .1, .1], [3, 0, .2, .2, .1, .1]])
     out = fd.shard_labels(labels, 2, 4)
     assert out[:, 0].tolist() == [0.0, 1.0] and out[:, 1].tolist() == [3.0, 0.0]
+
+
+def _agree_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import warnings
+
+    class _Fake:                                   # stands in for a PeerReducer whose construction worked on rank 0 only
+        def __init__(self, device, group=None):
+            if dist.get_rank() != 0:
+                raise RuntimeError("symmetric memory unavailable on this rank")
+
+    fd.PeerReducer = _Fake
+    fd._peer_reducers.clear()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        red = fd.peer_reducer(torch.device("cpu"), None)
+    q.put((rank, red is None, len(w)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_vs_nccl_choice_is_agreed_group_wide():
+    """If the peer-memory reducer cannot be built on ONE rank, EVERY rank must fall back to the NCCL all-reduce (a rank alone in the
+    peer kernel would wait for the others forever): the choice is the MIN of the per-rank success flags."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_agree_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [g[1] for g in got] == [True, True]                 # rank 0's own success does not count
+    assert all(g[2] >= 1 for g in got)                         # and both ranks say why
