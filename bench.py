@@ -857,7 +857,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="images in the bounded CPU-baseline sample")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--decode-event-every", type=int, default=8, help="bracket every n-th decode launch with timing events")
+    ap.add_argument("--decode-event-every", type=int, default=16, help="bracket every n-th decode launch with timing events")
     ap.add_argument("--no-unrolled-graph", action="store_true", help="time per-step launches instead of one K-step CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip config-5 mAP, dp_parity and config-3 strong scaling")
     args = ap.parse_args()
