@@ -584,3 +584,49 @@ def test_full_size_properties_config3_ship608():
         p += lossf.partials
     close(p, out["partials"], rtol=1e-9, atol=0)
     close(lossf.combine(p, batch, ctx=step.ctx), out["loss"])
+
+
+def test_full_size_properties_config3_b1024():
+    """BASELINE configs[2] at its FULL global batch (YOLOv3-608, 10 classes, B = 1024: 1.4 GB of heads, 23.3 M rows): what a single
+    GPU computes for the whole batch must be, image for image, what the 128-image shards of the 8-GPU run compute -- detections
+    bit-equal, loss partials additive over the shards -- plus oracle spot checks (decode rows, keep lists) on images of the first,
+    a middle and the last shard, and the NMS invariants on a stride of images."""
+    cfg, batch, shard = synth.SHIP608, 1024, 128
+    g = synth.make_generator(3)
+    labels = synth.make_labels(cfg, batch, g)
+    heads = synth.make_heads(cfg, batch, labels, g)
+    dh, dl = [h.cuda() for h in heads], labels.cuda()
+    full = ValStep(cfg.anchors_levels(), cfg.strides)
+    out = full(dh, dl)
+    torch.cuda.synchronize()
+    assert int(out["cnt"].min()) >= 0
+    part = ValStep(cfg.anchors_levels(), cfg.strides)
+    psum = torch.zeros(3, 4, dtype=torch.float64, device="cuda")
+    for lo in range(0, batch, shard):
+        o = part([h[lo:lo + shard].contiguous() for h in dh], shard_labels(dl, lo, lo + shard))
+        psum += o["partials"]
+        assert torch.equal(o["cnt"], out["cnt"][lo:lo + shard]), lo
+        valid = torch.arange(o["boxes"].size(1), device="cuda")[None, :] < o["cnt"][:, None]
+        for key in ("boxes", "scores", "cls"):
+            assert torch.equal(o[key][valid], out[key][lo:lo + shard][valid]), (lo, key)
+        if lo in (0, 512):
+            assert torch.equal(o["results"], out["results"][lo:lo + shard])
+    close(psum, out["partials"], rtol=1e-9, atol=0)                       # loss/yolov3_loss.py:52,58,64: sums are additive
+    close(full.loss_fn.combine(psum, batch, ctx=full.ctx), out["loss"])
+    pick = [5, 517, 1023]
+    want_res = oracle.decode.decode([h[pick] for h in heads], cfg.anchors_levels(), cfg.strides)
+    close(out["results"][pick], want_res)
+    res_cpu = out["results"][pick].cpu()
+    for j, i in enumerate(pick):
+        ws, wc, wb = on.nms_lib(res_cpu[j], 0.25, 0.45, 300)
+        k = int(out["cnt"][i])
+        assert k == ws.size(0)
+        assert np.array_equal(out["boxes"][i, :k].cpu().numpy(), wb.numpy())
+        assert np.array_equal(out["cls"][i, :k].cpu().numpy(), wc.view(-1).numpy())
+    for i in range(0, batch, 97):
+        k = int(out["cnt"][i])
+        s = out["scores"][i, :k]
+        assert bool((s[:-1] >= s[1:]).all())
+        iou = ft.cal_iou_batch(out["boxes"][i, :k].contiguous(), out["boxes"][i, :k].contiguous())
+        iou.fill_diagonal_(0)
+        assert float(iou.max()) <= 0.45 + 1e-6
