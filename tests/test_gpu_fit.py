@@ -224,3 +224,52 @@ def test_map_matcher_many_targets_and_padded_batches():
     ra, rb = a.fetch(), b.fetch()
     assert ra[2] == rb[2] and np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
     assert np.array_equal(np.concatenate(a.correct_all_images), np.concatenate(b.correct_all_images))
+
+
+def _evidence_reference(boxes, scores, cls, cnt, labels, w, h):
+    """utils/fit.py:96-99 per image, concatenated: detections [cls, conf, xyxy] and targets [cls, xyxy px] grouped by image."""
+    b = boxes.size(0)
+    dets, doff, gts, goff = [], [0], [], [0]
+    for i in range(b):
+        k = max(int(cnt[i]), 0)
+        dets.append(torch.cat([cls[i, :k].float()[:, None], scores[i, :k, None], boxes[i, :k]], 1))
+        doff.append(doff[-1] + k)
+        t = labels[labels[:, 0] == i][:, 1:]
+        half = t[:, 3:5] / 2
+        xyxy = torch.cat([t[:, 1:3] - half, t[:, 1:3] + half], 1) * torch.tensor([w, h, w, h], dtype=t.dtype)
+        gts.append(torch.cat([t[:, 0:1], xyxy], 1))
+        goff.append(goff[-1] + t.size(0))
+    return torch.cat(dets), doff, torch.cat(gts), goff
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_val_evidence_kernel_random_cases(seed):
+    """fvb_val_evidence_f32 against the per-image Python of utils/fit.py:94-99: empty images, images without labels, labels in
+    arbitrary order, labels of images outside the batch (dropped), a failed image (cnt = -1), no labels at all."""
+    from fastvision_b200 import _lib
+    g = torch.Generator().manual_seed(300 + seed)
+    b, md = int(torch.randint(1, 40, (1,), generator=g)), int(torch.randint(1, 50, (1,), generator=g))
+    t = 0 if seed == 5 else int(torch.randint(0, 200, (1,), generator=g))
+    boxes = torch.rand(b, md, 4, generator=g) * 400
+    scores = torch.rand(b, md, generator=g)
+    cls = torch.randint(0, 80, (b, md), generator=g)
+    cnt = torch.randint(0, md + 1, (b,), generator=g).int()
+    cnt[0] = -1 if seed % 2 else 0
+    img = torch.randint(0, b + (2 if seed % 3 == 0 else 0), (t,), generator=g).float()     # sometimes ids beyond the batch
+    if seed % 2 == 0:
+        img = torch.sort(img)[0]                                                              # collate order (fast path)
+    labels = torch.cat([img[:, None], torch.randint(0, 80, (t, 1), generator=g).float(), torch.rand(t, 4, generator=g)], 1)
+    w, h = 416.0, 320.0
+    want_d, want_doff, want_g, want_goff = _evidence_reference(boxes, scores, cls, cnt, labels, w, h)
+    db, ds, dc, dn, dl = boxes.cuda(), scores.cuda(), cls.cuda(), cnt.cuda(), labels.cuda()
+    dets = torch.full((b * md, 6), -7.0, device="cuda")
+    gts = torch.full((max(t, 1), 5), -7.0, device="cuda")
+    doff = torch.empty(b + 1, dtype=torch.int32, device="cuda")
+    goff = torch.empty(b + 1, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().fvb_val_evidence_f32(_lib.dptr(db), _lib.dptr(ds), _lib.dptr(dc), _lib.dptr(dn), b, md, _lib.dptr(dl), t,
+                                                w, h, _lib.dptr(dets), _lib.dptr(doff), _lib.dptr(gts), _lib.dptr(goff),
+                                                _lib.stream()), "val_evidence")
+    torch.cuda.synchronize()
+    assert doff.cpu().tolist() == want_doff and goff.cpu().tolist() == want_goff
+    assert torch.equal(dets[:want_doff[-1]].cpu(), want_d)
+    np.testing.assert_allclose(gts[:want_goff[-1]].cpu().numpy(), want_g.numpy(), rtol=1e-6, atol=1e-4)
