@@ -393,6 +393,53 @@ def strong_config3(rank, world, dev, dist, barrier, k=50):
     return res
 
 
+def other_configs_1gpu(dev, peak):
+    """BASELINE.json configs[2] and configs[3] on this one GPU, outside the timed region, so that a single-GPU bench record
+    carries every config's number: YOLOv3-608 / 10 classes / B=1024 step (the 1024 images are 8 copies of one seeded 128-image
+    block, as in strong_config3) and the Faster R-CNN RPN proposal filter at B=64 (demos/faster_rcnn/models/rpn.py:168-208)."""
+    from fastvision_b200.pipeline import ValStep
+    from fastvision_b200.detection import tools as ft
+    res = {}
+    cfg, total, block = synth.SHIP608, 1024, 128
+    g = synth.make_generator(3)
+    lab_b = synth.make_labels(cfg, block, g)
+    hb = [h.to(dev) for h in synth.make_heads(cfg, block, lab_b, g)]
+    heads = [h.repeat(total // block, 1, 1, 1, 1).contiguous() for h in hb]
+    labs = []
+    for c in range(total // block):
+        t = lab_b.clone()
+        t[:, 0] += c * block
+        labs.append(t)
+    labels = torch.cat(labs).to(dev)
+    step = ValStep(cfg.anchors_levels(), cfg.strides, data_parallel=False)
+    ms = time_step_loop(step, heads, labels, 30, dev, lambda: torch.cuda.synchronize(), True, False)
+    alg = 2 * total * step.ctx.rows * step.ctx.k * 4
+    res["config3_1gpu"] = {"workload": "YOLOv3-608, 10 classes, batch 1024 (BASELINE.json configs[2]) on one GPU", "ms_per_step": ms,
+                           "images_per_s": total / (ms * 1e-3), "algorithmic_GBps": alg / (ms * 1e-3) / 1e9,
+                           "frac_of_peak": alg / (ms * 1e-3) / 1e9 / peak, "nms_under_decode": bool(step.overlap_nms)}
+    del step, heads, labels, hb
+    torch.cuda.empty_cache()
+    gen = synth.make_generator(4)
+    cls, reg = synth.make_rpn_inputs(64, 50, 50, 9, gen)
+    dc, dr = cls.to(dev), reg.to(dev)
+    base = ft.get_base_anchor([128, 256, 512], [1, 0.5, 2]) / 16
+    rpn = {}
+    for pre, post in ((12000, 2000), (6000, 300), (2000, 2000)):
+        for _ in range(3):
+            ft.filter_proposals_batched(dc, dr, base, pre, post, 0.7)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            ft.filter_proposals_batched(dc, dr, base, pre, post, 0.7)
+        b.record()
+        torch.cuda.synchronize()
+        t = a.elapsed_time(b) / 10
+        rpn["pre%d_post%d" % (pre, post)] = {"ms": t, "images_per_s": 64 / (t * 1e-3)}
+    res["config4_rpn"] = dict(rpn, workload="Faster R-CNN RPN proposal filter, B=64, 22 500 anchors/image, nms 0.7 (BASELINE.json configs[3])")
+    return res
+
+
 def dp_parity(step, dh, dl, batch, rank, world, dev, dist, cfg):
     """Outside the timed region: the sharded step against ONE single-GPU step over the gathered global batch (rank 0).
     loss/yolov3_loss.py:52,58,64 normalise by GLOBAL counts, so the sharded loss must equal the full-batch loss (rtol 1e-6) and
@@ -788,6 +835,8 @@ def run_cuda(args, cfg):
         if distributed:
             extras["dp_parity"] = dp_parity(step, dh, dl, batch, rank, world, dev, dist, cfg)
             extras["strong_config3"] = strong_config3(rank, world, dev, dist, barrier)
+        else:
+            extras.update(other_configs_1gpu(dev, measured_peak_hbm()[0]))
     if unrolled is not None:
         step_launch = ("the K steps captured back to back in one CUDA graph (decode -> NMS branch || loss branch%s), every decode "
                        "kernel between its own pair of external timing-event nodes" %
