@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 from fastvision_b200 import synth  # noqa: E402
 
 METRIC = "images/sec YOLOv3-416 decode+NMS+loss"
+WORKLOAD = "YOLOv3-416 COCO-shape (80 cls, 3x3 anchors) decode+CIoU loss+NMS, batch 256 per GPU (BASELINE.json configs[1])"
 UNIT = "images/s"
 CONFIG_ID = 2
 
@@ -172,8 +173,11 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "YOLOv3-416 COCO-shape (80 cls, 3x3 anchors) decode+CIoU loss+NMS, batch 256 per GPU",
-                   "step_sample_images": sample, "timed_on": "host CPU"},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+                   "rows_per_image": cfg.cells, "channels": cfg.k, "conf_thres": 0.25, "iou_thres": 0.45, "max_det": 300,
+                   "loss_ratios": [0.05, 1.0, 0.5],
+                   "step_sample_images": sample, "timed_on": "host CPU",
+                   "note": "each step is a %d-image sample of the %d-image workload (same generator and seed), images/s-normalised" % (sample, args.batch)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample_desc, "cpu_model": cpu_model_name(), "stages": cpu_stage_baseline()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -860,8 +864,7 @@ def run_cuda(args, cfg):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms_max / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "YOLOv3-416 COCO-shape (80 cls, 3x3 anchors) decode+CIoU loss+NMS, batch 256 per GPU "
-                                   "(BASELINE.json configs[1])",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": batch, "global_batch": batch * world, "rows_per_image": rows, "channels": step.ctx.k,
                        "conf_thres": 0.25, "iou_thres": 0.45, "max_det": 300, "loss_ratios": [0.05, 1.0, 0.5],
                        "labels": int(labels.size(0)), "parallelism": "per-image sharding, dp%d" % world,
