@@ -475,7 +475,7 @@ extern "C" int fvb_yolo_nms_after_decode_f32(const float* d_results, int batch, 
   if (d_cand_bitmap) {
     p.bitmap = d_cand_bitmap;
     p.rec = d_cand_rec;
-    p.clear_bitmap = clear_bitmap;
+    p.clear_bitmap = clear_bitmap & FVB_NMS_CLEAR_BITMAP;
     FVB_REQUIRE(((uintptr_t)d_cand_rec & 15) == 0, "yolo_nms: candidate records must be 16-byte aligned");
   } else {
     p.bitmap = (uint32_t*)(w + o);
@@ -521,19 +521,26 @@ extern "C" int fvb_yolo_nms_after_decode_f32(const float* d_results, int batch, 
     count_launch();
     return check_launch("yolo_nms_kernel");
   }
-  int rc = ensure_smem((const void*)yolo_nms_kernel<true, 512>, L.total, "yolo_nms_after_decode");
+  // FVB_NMS_WIDE_CTA: the caller says no NMS CTA fits beside a decode CTA anyway (narrow rows) -- with at most one image per SM the
+  // CTAs then take 1024 threads and simply start, SM by SM, as the decode CTAs leave (no launch gap after the decode grid)
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+  const bool big = (clear_bitmap & FVB_NMS_WIDE_CTA) != 0 && batch <= sms;
+  const NmsSmemLayout L2 = nms_layout(kCapS, max_det, 32);
+  int rc = big ? ensure_smem((const void*)yolo_nms_kernel<true, 1024>, L2.total, "yolo_nms_after_decode")
+               : ensure_smem((const void*)yolo_nms_kernel<true, 512>, L.total, "yolo_nms_after_decode");
   if (rc != FVB_OK) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)batch);
-  cfg.blockDim = dim3(kNmsThreads);
-  cfg.dynamicSmemBytes = L.total;
+  cfg.blockDim = dim3(big ? 1024 : kNmsThreads);
+  cfg.dynamicSmemBytes = big ? L2.total : L.total;
   cfg.stream = cs;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, yolo_nms_kernel<true, 512>, p);
+  cudaError_t e = big ? cudaLaunchKernelEx(&cfg, yolo_nms_kernel<true, 1024>, p) : cudaLaunchKernelEx(&cfg, yolo_nms_kernel<true, 512>, p);
   if (e != cudaSuccess) {
     set_error("yolo_nms_after_decode: launch failed: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();

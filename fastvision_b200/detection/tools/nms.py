@@ -12,7 +12,7 @@ from ... import _lib
 
 def non_max_suppression_batched(results, conf_thres=0.25, iou_thres=0.45, max_det=300, flavour="lib",
                                 cand_bitmap=None, cand_records=None, clear_bitmap=True, max_wh=4096.0,
-                                want_rows=False, out=None, tile_sync=None, tiles_per_image=0, ws=None):
+                                want_rows=False, out=None, tile_sync=None, tiles_per_image=0, ws=None, wide_cta=False):
     """results [B,N,K] decoded -> (boxes[B,max_det,4] xyxy, scores[B,max_det], cls[B,max_det] i64, cnt[B] i32[, rows]).
 
     Entries past cnt[b] are undefined.  ``cand_bitmap`` / ``cand_records`` are the [B, ceil(N/32)] int32 bitmap
@@ -21,6 +21,7 @@ def non_max_suppression_batched(results, conf_thres=0.25, iou_thres=0.45, max_de
     ``tile_sync`` / ``tiles_per_image`` (``DecodeContext.tile_sync()`` / ``.tiles_per_image``): this call follows the
     ``yolov3_decode(..., tile_sync=...)`` launch of the same tensors DIRECTLY on the current stream and is launched as its
     programmatic dependent -- image b's NMS starts as soon as image b is decoded (``fvb_yolo_nms_after_decode_f32``).
+    ``wide_cta`` (with ``tile_sync``): the decode geometry leaves no room for an NMS CTA beside a decode CTA (FVB_NMS_WIDE_CTA).
     ``ws``: caller-owned workspace (uint8, >= ``fvb_yolo_nms_workspace_bytes``) instead of the process-wide scratch.
     """
     results = _lib.require_cuda(results, "results")
@@ -45,7 +46,8 @@ def non_max_suppression_batched(results, conf_thres=0.25, iou_thres=0.45, max_de
     with torch.cuda.device(dev):
         _lib.check(lib.fvb_yolo_nms_after_decode_f32(_lib.dptr(results), b, n, k, float(conf_thres), float(iou_thres), int(max_det),
                                                      _lib.NMS_FLAVOURS[flavour], float(max_wh), _lib.dptr(cand_bitmap),
-                                                     _lib.dptr(cand_records), 1 if clear_bitmap else 0, _lib.dptr(boxes),
+                                                     _lib.dptr(cand_records), (1 if clear_bitmap else 0) | (2 if wide_cta else 0),
+                                                     _lib.dptr(boxes),
                                                      _lib.dptr(scores), _lib.dptr(cls), _lib.dptr(rows), _lib.dptr(cnt),
                                                      _lib.dptr(tile_sync), int(tiles_per_image) if tile_sync is not None else 0,
                                                      _lib.dptr(ws), _lib.stream()), "yolo_nms")

@@ -75,8 +75,14 @@ class ValStep:
         ctx.records()
         ctx.bce0()
         ctx.tile_sync()
+        room = _lib.load().fvb_yolo_decode_leaves_room_for_nms(ctx.geom) == 1
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        # no room (narrow rows): the pair still pays for at most one image per SM -- 1024-thread NMS CTAs that start, SM by SM, as
+        # the decode CTAs leave instead of after the decode grid + a launch gap (608 / C=10 / 128 images: 0.1074 -> 0.1050 ms)
+        self._wide_cta = not room
         if self._overlap_request is None:
-            self.overlap_nms = _lib.load().fvb_yolo_decode_leaves_room_for_nms(ctx.geom) == 1
+            self.overlap_nms = room or b <= sms
+        self._room = room
         self._nms_ws = self._ws.get("yolo_nms", _lib.load().fvb_yolo_nms_workspace_bytes(b, ctx.rows), dev)
         self.graph = None
         # NMS (latency-bound, one CTA per image) and the loss kernels only depend on the decode: they run as
@@ -99,7 +105,7 @@ class ValStep:
         A single GPU with a geometry that cannot overlap (narrow rows) keeps the one-call loss after the decode, where the long
         NMS phase hides it completely; launched in front of the decode its CTAs only delay the decode's start (608 / C=10 /
         B=1024: 0.742 vs 0.72 ms)."""
-        return self.overlap_nms or self._distributed()
+        return (self.overlap_nms and self._room) or self._distributed()
 
     def _head(self, heads, labels):
         """First launches of a step: the loss's target assignment + matched-row terms read only the RAW heads and the labels,
@@ -124,7 +130,8 @@ class ValStep:
         non_max_suppression_batched(o["results"], self.conf_thres, self.iou_thres, self.max_det, self.nms_flavour,
                                     cand_bitmap=ctx.bitmap(), cand_records=ctx.records(), clear_bitmap=True,
                                     out=(o["boxes"], o["scores"], o["cls"], o["cnt"], o["rows"]),
-                                    tile_sync=sync, tiles_per_image=ctx.tiles_per_image, ws=self._nms_ws)
+                                    tile_sync=sync, tiles_per_image=ctx.tiles_per_image, ws=self._nms_ws,
+                                    wide_cta=self._wide_cta and self.overlap_nms)
 
     def _tail(self, heads, labels, reduce_inside=False):
         """Everything after the decode launch (``_head`` and ``_decode`` came first): the NMS kernel directly behind the decode

@@ -56,6 +56,9 @@ extern "C" {
 #define FVB_NMS_LIB 0        /* detection/tools/NMS.py:5-23, class-agnostic, rank by max_c(cls*obj), boxes xywh */
 #define FVB_NMS_DEMO 1       /* demos/yolov3_u/utils/nms.py:5-53, class-aware gap trick, rank by obj, boxes xyxy */
 #define FVB_NMS_DEMO_BATCH 2 /* demos/yolov3_u/utils/nms.py:55-98, class-aware, rank by max_c(cls*obj), boxes xywh */
+/* flag bits of the `clear_bitmap` argument of the fvb_yolo_nms_* calls (1 = the v1 meaning) */
+#define FVB_NMS_CLEAR_BITMAP 1 /* zero the candidate words the kernel consumed (ready for the next decode) */
+#define FVB_NMS_WIDE_CTA 2     /* fvb_yolo_nms_after_decode_f32 only: fvb_yolo_decode_leaves_room_for_nms() said 0 */
 /* reductions */
 #define FVB_REDUCE_MEAN 0
 #define FVB_REDUCE_SUM 1
@@ -192,7 +195,9 @@ int fvb_yolo_nms_f32(const float* d_results, int batch, int rows_per_image, int 
 /* The same call as the consumer of fvb_yolo_decode_sync_f32 (same d_tile_sync, tiles_per_image =
  * fvb_yolo_decode_tiles_per_image(geom), same d_cand_bitmap / d_cand_rec, enqueued directly behind it on the same stream): the
  * kernel is launched as a PROGRAMMATIC DEPENDENT of the decode kernel, so image b's NMS starts as soon as image b is decoded
- * and only the images decoded last remain when the decode kernel exits.  Results are identical to fvb_yolo_nms_f32.  If the
+ * and only the images decoded last remain when the decode kernel exits.  Results are identical to fvb_yolo_nms_f32.  When no NMS
+ * CTA fits beside a decode CTA (fvb_yolo_decode_leaves_room_for_nms() == 0) the pair still saves the launch gap for batches of at
+ * most one image per SM: pass FVB_NMS_WIDE_CTA in clear_bitmap and the CTAs (1024 threads then) start SM by SM as decode CTAs leave.  If the
  * decode launch is missing the kernel gives up after ~4 s and writes d_out_cnt[b] = -1 (it never hangs the device). */
 int fvb_yolo_nms_after_decode_f32(const float* d_results, int batch, int rows_per_image, int channels, float conf_thr,
                                   double iou_thr, int max_det, int flavour, float max_wh, uint32_t* d_cand_bitmap,
