@@ -78,10 +78,12 @@ class ValStep:
         room = _lib.load().fvb_yolo_decode_leaves_room_for_nms(ctx.geom) == 1
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         # no room (narrow rows): the pair still pays for at most one image per SM -- 1024-thread NMS CTAs that start, SM by SM, as
-        # the decode CTAs leave instead of after the decode grid + a launch gap (608 / C=10 / 128 images: 0.1074 -> 0.1050 ms)
+        # the decode CTAs leave instead of after the decode grid + a launch gap (608 / C=10 / 128 images: 0.1083 -> 0.1040 ms).
+        # Not under data parallelism: whole-SM NMS CTAs that arrive that early leave the loss finish + peer reduce no SM to run
+        # on until they are done (2 ranks x 128 images: 0.1115 vs 0.1035-0.1070 ms with the plain launch).
         self._wide_cta = not room
         if self._overlap_request is None:
-            self.overlap_nms = room or b <= sms
+            self.overlap_nms = room or (b <= sms and not self._distributed())
         self._room = room
         self._nms_ws = self._ws.get("yolo_nms", _lib.load().fvb_yolo_nms_workspace_bytes(b, ctx.rows), dev)
         self.graph = None
